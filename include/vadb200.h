@@ -1,0 +1,129 @@
+/*
+ * vadb200.h -- C ABI of libvadb200.so, the B200 (sm_100a) implementation of the
+ * Self-Attentive VAD inference hot path of voithru/voice-activity-detection.
+ *
+ * The reference has no native layer (it is pure Python/PyTorch), so there is no existing
+ * FFI to mirror: each entry point below names the reference *Python* interface it
+ * replaces (paths relative to the reference repository root).  Plain pointers and sizes
+ * only; no torch types.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative VADB_E_* code on failure;
+ *     vadb_last_error(h) gives the message (the Python wrapper raises RuntimeError).
+ *   - "dev" pointers are CUDA device pointers on the handle's device; `stream` is a
+ *     cudaStream_t passed as void* (0 = legacy default stream).  Calls taking a stream
+ *     are asynchronous on it and never synchronise internally, except where they must
+ *     grow the handle-owned workspace (first call with a larger B*T; use vadb_reserve
+ *     to take that out of the steady state).
+ *   - the caller owns inputs/outputs; the library owns weights, the positional-encoding
+ *     table and the workspace inside the handle.  One handle per device; a handle is not
+ *     thread-safe, distinct handles are independent.
+ *   - there is NO CPU fallback: without a CUDA device vadb_create fails.
+ */
+#ifndef VADB200_H_
+#define VADB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vadb_handle vadb_handle;
+
+enum { VADB_F32 = 0, VADB_BF16 = 1 };           /* dtypes (input tensors / compute mode) */
+
+enum {
+  VADB_OK = 0,
+  VADB_E_INVALID = -1,     /* bad argument / unsupported configuration */
+  VADB_E_CUDA = -2,        /* CUDA runtime or driver error */
+  VADB_E_STATE = -3,       /* e.g. forward before weights were loaded */
+  VADB_E_NOMEM = -4
+};
+
+/* Model hyper-parameters.  Replaces the arguments of
+ * vad/models/self_attention.py:7 SelfAttentiveVAD(feature_size, num_layers, d_model, dropout)
+ * as selected by vad/models/model_factory.py:42-48 from the checkpoint's config
+ * (vad/configs/model_config.py:8-35).  dropout is an eval-time identity and is dropped.
+ * The kernels are specialised for d_model == 128 (d_ff == 512, n_heads == 1), the only
+ * values the reference instantiates; anything else is VADB_E_INVALID. */
+typedef struct {
+  int32_t feature_size;    /* F: n_mels (80 in the reference checkpoint, 64 in BASELINE) */
+  int32_t num_layers;      /* L */
+  int32_t d_model;         /* must be 128 */
+  int32_t compute_dtype;   /* VADB_F32: fp32 CUDA-core path (<=1e-3 parity);
+                              VADB_BF16: bf16 tensor-core operands, fp32 accumulate/residual/LN/softmax */
+} vadb_config;
+
+/* ---- lifecycle: replaces VADFromScratchPredictor.from_checkpoint's model construction +
+ *      load_state_dict + .to(device)  (vad/predictor.py:264-280) ---- */
+int vadb_create(vadb_handle** out, const vadb_config* cfg, int device);
+void vadb_destroy(vadb_handle* h);
+const char* vadb_last_error(const vadb_handle* h);   /* h may be NULL: last create error */
+
+/* Number of fp32 elements of the packed weight blob for a config, and the element offset
+ * of a named tensor inside it.  Order = the reference state_dict order
+ * (vad/predictor.py:278 load_state_dict; names listed in SURVEY.md section 8 a1), each
+ * tensor row-major in nn.Linear [out,in] layout. */
+size_t vadb_weight_count(const vadb_config* cfg);
+
+/* Load the packed fp32 blob (host pointer when on_device == 0, device pointer otherwise --
+ * e.g. the buffer a rank received from the one-off NCCL weight broadcast) and derive the
+ * kernel-side copies (bf16 / fused QKV / classifier).  Synchronises `stream` before return. */
+int vadb_load_weights(vadb_handle* h, const float* blob, size_t count, int on_device, void* stream);
+
+/* Pre-size the workspace (and positional-encoding table) for calls up to B clips x T frames. */
+int vadb_reserve(vadb_handle* h, int B, int T);
+
+/* ---- hot path: replaces SelfAttentiveVAD.forward (vad/models/self_attention.py:23-28)
+ *      + the caller's softmax(...)[...,1] (vad/predictor.py:225,257-258).
+ *  x        dev [B,T,F] contiguous, x_dtype VADB_F32 or VADB_BF16
+ *  lengths  dev int32 [B] or NULL; key-padding mask j >= lengths[b] as built by
+ *           mask_from_lengths (vad/modeling/transformer.py:432-447, :319-325)
+ *  prob     dev float [B,T]   P(speech) = softmax(logp)[1]           (or NULL)
+ *  logp     dev float [B,T,2] the module's log_softmax output         (or NULL)        */
+int vadb_forward(vadb_handle* h, const void* x, int x_dtype, const int32_t* lengths,
+                 int B, int T, float* prob, float* logp, void* stream);
+
+/* Same call with HOST buffers (pageable or pinned): the library stages them through its
+ * pinned buffers, copies H2D, runs the forward and copies the results D2H, on its own
+ * stream, and returns when the outputs are in host memory.  This is the end-to-end
+ * entry the reference-facing wrapper uses for numpy / CPU-tensor inputs
+ * (vad/predictor.py:223 .to(device), :247 .cpu()). */
+int vadb_forward_host(vadb_handle* h, const float* x, const int32_t* lengths, int B, int T,
+                      float* prob, float* logp);
+
+/* ---- replaces VADFromScratchPredictor.predict_probabilities from the feature matrix on
+ *      (vad/predictor.py:169-262): window gather (:180-220), batched forward (:221-225)
+ *      and boosted aggregation incl. the 0.5 fill of never-written slots (:238-258).
+ *  feat       dev float [L,F]  log-mel frames
+ *  probs_LW   dev float [L,W]  W = 2*(half-1)/jump + 3           (or NULL)
+ *  mean_L     dev float [L]    probs.mean(axis=1) (vad/predictor.py:95)  (or NULL)     */
+int vadb_predict_probabilities(vadb_handle* h, const float* feat, int L, int half, int jump,
+                               float* probs_LW, float* mean_L, void* stream);
+int vadb_predict_probabilities_host(vadb_handle* h, const float* feat, int L, int half,
+                                    int jump, float* probs_LW, float* mean_L);
+
+/* ---- individual stages, exported for kernel-level parity tests and the roofline bench ---- */
+/* Fused scaled-dot-product attention over the frame axis:
+ * O = softmax(Q K^T / sqrt(128) [+ key padding mask]) V   (vad/modeling/transformer.py:351-363,
+ * :319-346), one head, d_head = 128.  q,k,v,o dev [B,T,128] contiguous, dtype VADB_F32 or
+ * VADB_BF16 (bf16 -> tcgen05 kernel; fp32 -> CUDA-core kernel). */
+int vadb_attention(vadb_handle* h, const void* q, const void* k, const void* v, void* o,
+                   int dtype, const int32_t* lengths, int B, int T, void* stream);
+
+/* Positional-encoding table PE[t, :]/sqrt(d) the library adds in the front end
+ * (vad/modeling/transformer.py:392-414); copies T*128 floats to a host buffer. */
+int vadb_positional_table(vadb_handle* h, int T, float* out_host);
+
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+int64_t vadb_launch_count(const vadb_handle* h);
+
+/* Library / build identification, e.g. "vadb200 0.1 sm_100a". */
+const char* vadb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VADB200_H_ */

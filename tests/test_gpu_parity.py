@@ -1,0 +1,204 @@
+"""GPU parity: the CUDA path (through the C ABI) against the real-reference golden vectors
+and the oracle on the same seeded inputs.  Tolerances are the north-star ones:
+per-frame P(speech) within 1e-3 (fp32 path) / 1e-2 (bf16 path) of the reference CPU fp32."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vad_oracle as O
+from tests.golden_util import (golden, model_cases, predictor_cases, prob_from_logp,
+                               sample_checkpoint_state, valid_mask)
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-3, "bf16": 1e-2}
+CASES = model_cases()
+_engines = {}
+
+
+def SYN():
+    return O.make_state(0, 64, 3, 128)
+
+
+def engine_for(state_factory, dtype):
+    """One engine per (weights, dtype) for the whole module (state factories are module-level)."""
+    from vad_b200.engine import VadEngine
+    key = (id(state_factory), dtype)
+    if key not in _engines:
+        _engines[key] = VadEngine.from_state_dict(state_factory(), compute_dtype=dtype)
+    return _engines[key]
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_forward_vs_reference_golden(name, dtype):
+    mk_state, mk_x, len_key = CASES[name]
+    g = golden()
+    lengths = g[len_key] if len_key else None
+    eng = engine_for(mk_state, dtype)
+    x = mk_x().cuda()
+    ln = torch.as_tensor(lengths, dtype=torch.int32).cuda() if lengths is not None else None
+    prob, logp = eng.forward(x, ln)
+    torch.cuda.synchronize()
+    want_logp = g[name]
+    m = valid_mask(want_logp.shape[:2], lengths)
+    want_p = prob_from_logp(want_logp)
+    err_p = np.abs(prob.cpu().numpy() - want_p)[m].max()
+    err_lp = np.abs(logp.cpu().numpy() - want_logp)[m].max()
+    print(f"{name} {dtype}: max|dP|={err_p:.3e} max|dlogp|={err_lp:.3e}")
+    assert np.isfinite(prob.cpu().numpy()[m]).all()
+    assert err_p <= TOL[dtype]
+    # log-probs: same bound scaled by the steepest slope of log around p ~ [0.05, 0.95]
+    assert err_lp <= 20 * TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_forward_vs_oracle_seeded(dtype):
+    st = O.make_state(5, 64, 3, 128)
+    from vad_b200.engine import VadEngine
+    eng = VadEngine.from_state_dict(st, compute_dtype=dtype)
+    for (B, T) in [(1, 7), (3, 65), (2, 129), (5, 256), (1, 513)]:
+        x = O.make_input(100 + T, B, T, 64)
+        want = O.forward_prob(st, x).numpy()
+        prob, _ = eng.forward(x.cuda(), want_logp=False)
+        err = np.abs(prob.cpu().numpy() - want).max()
+        print(f"B={B} T={T} {dtype}: {err:.3e}")
+        assert err <= TOL[dtype]
+    eng.close()
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_bf16_input_tensor(dtype):
+    st = O.make_state(6, 64, 3, 128)
+    from vad_b200.engine import VadEngine
+    eng = VadEngine.from_state_dict(st, compute_dtype=dtype)
+    x = O.make_input(7, 2, 128, 64).to(torch.bfloat16)
+    want = O.forward_prob(st, x.to(torch.float32)).numpy()   # same (rounded) inputs
+    prob, _ = eng.forward(x.cuda(), want_logp=False)
+    assert np.abs(prob.cpu().numpy() - want).max() <= TOL[dtype]
+    eng.close()
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_host_call_matches_device_call(dtype):
+    st = O.make_state(0, 64, 3, 128)
+    from vad_b200.engine import VadEngine
+    eng = VadEngine.from_state_dict(st, compute_dtype=dtype)
+    x = O.make_input(1, 4, 512, 64)
+    lengths = torch.tensor([512, 100, 512, 333], dtype=torch.int32)
+    p_dev, lp_dev = eng.forward(x.cuda(), lengths.cuda())
+    p_host, lp_host = eng.forward(x, lengths)           # CPU tensors -> vadb_forward_host
+    assert not p_host.is_cuda
+    np.testing.assert_array_equal(p_host.numpy(), p_dev.cpu().numpy())
+    np.testing.assert_array_equal(lp_host.numpy(), lp_dev.cpu().numpy())
+    eng.close()
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", sorted(predictor_cases()))
+def test_predict_probabilities_vs_reference_golden(name, dtype):
+    feat = predictor_cases()[name]()
+    eng = engine_for(sample_checkpoint_state, dtype)
+    probs, mean = eng.predict_probabilities(feat, 19, 9)
+    want = golden()[name]
+    assert probs.shape == want.shape
+    err = np.abs(probs - want).max()
+    print(f"{name} {dtype}: {err:.3e}")
+    assert err <= TOL[dtype]
+    np.testing.assert_allclose(mean, probs.mean(axis=1), atol=1e-6)
+    # never-written slots are EXACTLY 0.5 (vad/predictor.py:239-258)
+    np.testing.assert_array_equal(probs[want == 0.5], 0.5)
+    # device-resident variant gives the same numbers
+    p2, m2 = eng.predict_probabilities(torch.from_numpy(feat).cuda(), 19, 9)
+    np.testing.assert_array_equal(p2.cpu().numpy(), probs)
+
+
+def _ref_attention(q, k, v, lengths):
+    qf, kf, vf = q.double(), k.double(), v.double()
+    s = qf @ kf.transpose(1, 2) / np.sqrt(128.0)
+    if lengths is not None:
+        T = q.shape[1]
+        mask = torch.arange(T, device=q.device)[None, :] >= lengths[:, None].to(q.device)
+        s = s.masked_fill(mask[:, None, :], float("-inf"))
+    return torch.softmax(s, dim=-1) @ vf
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("B,T,masked", [(2, 512, False), (3, 300, True), (1, 64, False), (5, 7, False),
+                                        (2, 1, False), (1, 2048, True), (4, 129, True)])
+def test_attention_kernel(B, T, masked, dtype, tol):
+    from vad_b200.engine import VadEngine
+    eng = engine_for(SYN, "bf16" if dtype == torch.bfloat16 else "fp32")
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    q = (torch.randn(B, T, 128, generator=g) * 1.5).to(dtype).cuda()
+    k = (torch.randn(B, T, 128, generator=g) * 1.5).to(dtype).cuda()
+    v = torch.randn(B, T, 128, generator=g).to(dtype).cuda()
+    lengths = None
+    if masked:
+        lengths = torch.randint(1, T + 1, (B,), generator=g).to(torch.int32).cuda()
+        lengths[0] = T
+    o = eng.attention(q, k, v, lengths)
+    want = _ref_attention(q, k, v, lengths)
+    err = (o.double() - want).abs().max().item()
+    print(f"attn B={B} T={T} masked={masked} {dtype}: {err:.3e}")
+    assert err <= tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_attention_online_softmax_rescale(dtype):
+    """Scores that grow along the key axis force the running max to move in every KV tile."""
+    eng = engine_for(SYN, "bf16" if dtype == torch.bfloat16 else "fp32")
+    B, T = 2, 512
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(B, T, 128, generator=g)
+    k = torch.randn(B, T, 128, generator=g)
+    ramp = torch.linspace(0, 6, T)[None, :, None]
+    k = k + ramp * q.mean(dim=1, keepdim=True).sign()          # later keys align with the queries
+    q = q * 2
+    v = torch.randn(B, T, 128, generator=g)
+    q, k, v = (t.to(dtype).cuda() for t in (q, k, v))
+    o = eng.attention(q, k, v)
+    want = _ref_attention(q, k, v, None)
+    err = (o.double() - want).abs().max().item()
+    print(f"rescale {dtype}: {err:.3e}")
+    assert err <= (2e-5 if dtype == torch.float32 else 3e-2)
+
+
+def test_fully_masked_clip_is_nan_like_reference():
+    eng = engine_for(SYN, "fp32")
+    q = torch.randn(2, 64, 128).cuda()
+    o = eng.attention(q, q, q, torch.tensor([64, 0], dtype=torch.int32).cuda())
+    assert torch.isfinite(o[0]).all() and torch.isnan(o[1]).all()
+
+
+def test_positional_table_matches_oracle():
+    eng = engine_for(SYN, "fp32")
+    for T in (7, 512, 8192):
+        got = eng.positional_table(T)
+        want = (O.positional_encoding(T, 128)[0] / np.sqrt(128.0)).numpy()
+        # 1-ulp differences of exp() are amplified by t (<= 8191): well inside the 1e-3 budget
+        assert np.abs(got - want).max() <= 1e-4
+        assert np.abs(got[:64] - want[:64]).max() <= 2e-6
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 size (B=256, T=512, F=64, bf16): size-independent properties --
+    per-clip independence (a clip's result does not depend on its batch neighbours), batch
+    permutation equivariance, and probabilities in [0, 1] with logp rows normalised."""
+    st = O.make_state(0, 64, 3, 128)
+    from vad_b200.engine import VadEngine
+    eng = VadEngine.from_state_dict(st, compute_dtype="bf16")
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(256, 512, 64, generator=g) * 2 - 3).cuda()
+    prob, logp = eng.forward(x)
+    assert torch.isfinite(prob).all() and (prob >= 0).all() and (prob <= 1).all()
+    assert (logp.exp().sum(-1) - 1).abs().max().item() < 1e-5
+    perm = torch.randperm(256, generator=g).cuda()
+    prob_p, _ = eng.forward(x[perm].contiguous(), want_logp=False)
+    assert torch.equal(prob_p, prob[perm])
+    sub, _ = eng.forward(x[17:19].contiguous(), want_logp=False)
+    assert torch.equal(sub, prob[17:19])
+    # and the first clips agree with the oracle
+    want = O.forward_prob(st, x[:2].cpu()).numpy()
+    assert np.abs(prob[:2].cpu().numpy() - want).max() <= 1e-2
+    eng.close()

@@ -1,0 +1,532 @@
+// C ABI of libvadb200.so (see include/vadb200.h): handle, weights, workspace and the
+// orchestration of the forward pass / predictor window path on a caller-provided stream.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "vadb_common.cuh"
+
+namespace vadb {
+
+BlobLayout make_layout(int F, int L) {
+  // state_dict order of SelfAttentiveVAD (vad/models/self_attention.py:12-21,
+  // vad/modeling/transformer.py:40-47,245-248,230,370-375,22)
+  BlobLayout lay;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += n; return r; };
+  lay.w_in = take((size_t)D * F);
+  lay.b_in = take(D);
+  lay.layers.resize(L);
+  for (int l = 0; l < L; ++l) {
+    LayerOffsets& lo = lay.layers[l];
+    lo.wq = take((size_t)D * D); lo.bq = take(D);
+    lo.wk = take((size_t)D * D); lo.bk = take(D);
+    lo.wv = take((size_t)D * D); lo.bv = take(D);
+    lo.wo = take((size_t)D * D); lo.bo = take(D);
+    lo.ln1_g = take(D); lo.ln1_b = take(D);
+    lo.w1 = take((size_t)DFF * D); lo.b1 = take(DFF);
+    lo.w2 = take((size_t)D * DFF); lo.b2 = take(D);
+    lo.ln2_g = take(D); lo.ln2_b = take(D);
+  }
+  lay.lnf_g = take(D); lay.lnf_b = take(D);
+  lay.wc = take(2 * D); lay.bc = take(2);
+  lay.total = o;
+  return lay;
+}
+
+}  // namespace vadb
+
+using namespace vadb;
+
+struct vadb_handle {
+  vadb_config cfg;
+  int device = 0;
+  BlobLayout lay;
+  bool loaded = false;
+  std::string err;
+  int64_t launches = 0;
+
+  float* w32 = nullptr;      // packed fp32 blob (device)
+  float* wqkv = nullptr;     // [L][384*128] fused Q|K|V weight rows
+  float* bqkv = nullptr;     // [L][384]
+  bf16* wqkv_bf = nullptr;   // bf16 copies for the tensor-core kernels
+  bf16* wo_bf = nullptr;     // [L][128*128]
+  bf16* w1_bf = nullptr;     // [L][512*128]
+  bf16* w2_bf = nullptr;     // [L][128*512]
+
+  float* pe = nullptr;       // [pe_T, 128] = PE / sqrt(d)
+  int pe_T = 0;
+
+  // workspace, sized in frames
+  size_t cap_frames = 0;
+  float* ws_h = nullptr;
+  void* ws_q = nullptr; void* ws_k = nullptr; void* ws_v = nullptr; void* ws_o = nullptr;
+  float* ws_hid = nullptr;
+  float* ws_prob = nullptr;
+
+  // host-call staging
+  cudaStream_t own_stream = nullptr;
+  void* pin_in = nullptr; size_t pin_in_bytes = 0;
+  void* pin_out = nullptr; size_t pin_out_bytes = 0;
+  void* dev_in = nullptr; size_t dev_in_bytes = 0;
+  void* dev_out = nullptr; size_t dev_out_bytes = 0;
+  int32_t* dev_len = nullptr; size_t dev_len_n = 0;
+  void* win_prob = nullptr; size_t win_prob_bytes = 0;   // [n, W] per-window probabilities
+};
+
+namespace {
+
+std::string g_create_err;
+
+constexpr size_t MAX_FRAMES_PER_PASS = (size_t)1 << 20;
+
+int fail(vadb_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_err = msg;
+  return code;
+}
+
+#define CU_TRY(h, expr)                                                                      \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return fail((h), VADB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+bool is_bf16_mode(const vadb_handle* h) { return h->cfg.compute_dtype == VADB_BF16; }
+
+template <typename T>
+void free_dev(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
+
+int ensure_pe(vadb_handle* h, int T) {
+  if (T <= h->pe_T) return VADB_OK;
+  int newT = std::max(T, std::max(16, h->pe_T * 2));
+  // vad/modeling/transformer.py:403-414, then "/ self.scale" (:390, :401); all in fp32
+  std::vector<float> tab((size_t)newT * D);
+  const float c = (float)(-(log(10000.0) / (double)D));
+  const float scale = (float)sqrt((double)D);
+  for (int i = 0; i < D / 2; ++i) {
+    const float arg = (float)(2 * i) * c;
+    const float div = (float)exp((double)arg);
+    for (int t = 0; t < newT; ++t) {
+      const float ang = (float)t * div;
+      tab[(size_t)t * D + 2 * i] = (float)sin((double)ang) / scale;
+      tab[(size_t)t * D + 2 * i + 1] = (float)cos((double)ang) / scale;
+    }
+  }
+  // the table may be in use by work already queued on a caller stream: sync before replacing
+  CU_TRY(h, cudaDeviceSynchronize());
+  free_dev(h->pe);
+  CU_TRY(h, cudaMalloc(&h->pe, tab.size() * sizeof(float)));
+  CU_TRY(h, cudaMemcpy(h->pe, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->pe_T = newT;
+  return VADB_OK;
+}
+
+int ensure_workspace(vadb_handle* h, size_t frames) {
+  if (frames <= h->cap_frames) return VADB_OK;
+  size_t cap = std::max(frames, h->cap_frames + h->cap_frames / 2);
+  CU_TRY(h, cudaDeviceSynchronize());
+  free_dev(h->ws_h); free_dev(h->ws_q); free_dev(h->ws_k); free_dev(h->ws_v); free_dev(h->ws_o);
+  free_dev(h->ws_hid); free_dev(h->ws_prob);
+  h->cap_frames = 0;
+  const size_t act = is_bf16_mode(h) ? sizeof(bf16) : sizeof(float);
+  CU_TRY(h, cudaMalloc(&h->ws_h, cap * D * sizeof(float)));
+  CU_TRY(h, cudaMalloc(&h->ws_q, cap * D * act));
+  CU_TRY(h, cudaMalloc(&h->ws_k, cap * D * act));
+  CU_TRY(h, cudaMalloc(&h->ws_v, cap * D * act));
+  CU_TRY(h, cudaMalloc(&h->ws_o, cap * D * act));
+  CU_TRY(h, cudaMalloc(&h->ws_hid, cap * DFF * sizeof(float)));
+  CU_TRY(h, cudaMalloc(&h->ws_prob, cap * sizeof(float)));
+  h->cap_frames = cap;
+  return VADB_OK;
+}
+
+// clips per pass so that one pass stays within the workspace cap
+int clips_per_pass(int B, int T) {
+  size_t c = MAX_FRAMES_PER_PASS / (size_t)std::max(T, 1);
+  if (c < 1) c = 1;
+  return (int)std::min<size_t>(c, (size_t)B);
+}
+
+int gemm(vadb_handle* h, const GemmArgs& a, cudaStream_t s) {
+  cudaError_t e = launch_gemm_f32(a, s);
+  if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("gemm_f32: ") + cudaGetErrorString(e));
+  h->launches++;
+  return VADB_OK;
+}
+
+int attention(vadb_handle* h, const void* q, const void* k, const void* v, void* o, int dtype,
+              const int32_t* lengths, int B, int T, cudaStream_t s) {
+  if (dtype == VADB_BF16) {
+    std::string err;
+    cudaError_t e = launch_attn_tc((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, lengths,
+                                   B, T, s, &err);
+    if (e != cudaSuccess)
+      return fail(h, VADB_E_CUDA, std::string("attn_tc: ") + cudaGetErrorString(e) + " " + err);
+  } else {
+    cudaError_t e = launch_attn_f32((const float*)q, (const float*)k, (const float*)v, (float*)o,
+                                    lengths, B, T, s);
+    if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("attn_f32: ") + cudaGetErrorString(e));
+  }
+  h->launches++;
+  return VADB_OK;
+}
+
+// encoder layers + classifier over `Bc` clips of `T` frames whose front-end output is in ws_h
+int run_encoder(vadb_handle* h, const int32_t* lengths, int Bc, int T, float* prob, float* logp,
+                cudaStream_t s) {
+  const int M = Bc * T;
+  const float* w = h->w32;
+  const bool bf = is_bf16_mode(h);
+  for (int l = 0; l < h->cfg.num_layers; ++l) {
+    const LayerOffsets& lo = h->lay.layers[l];
+    int rc;
+    {  // a = LN1(h); q,k,v = a W^T + b        (transformer.py:235-236, :281-284)
+      GemmArgs g = {};
+      g.A = h->ws_h; g.W = h->wqkv + (size_t)l * 3 * D * D; g.bias = h->bqkv + (size_t)l * 3 * D;
+      g.M = M; g.N = 3 * D; g.K = D;
+      g.ln_g = w + lo.ln1_g; g.ln_b = w + lo.ln1_b;
+      g.out[0] = h->ws_q; g.out[1] = h->ws_k; g.out[2] = h->ws_v; g.out_split = D;
+      g.out_is_bf16 = bf;
+      if ((rc = gemm(h, g, s))) return rc;
+    }
+    if ((rc = attention(h, h->ws_q, h->ws_k, h->ws_v, h->ws_o, bf ? VADB_BF16 : VADB_F32, lengths,
+                        Bc, T, s)))
+      return rc;
+    {  // h += o Wo^T + bo                      (transformer.py:347, :237)
+      GemmArgs g = {};
+      g.A = h->ws_o; g.a_is_bf16 = bf; g.W = w + lo.wo; g.bias = w + lo.bo;
+      g.M = M; g.N = D; g.K = D; g.residual = h->ws_h;
+      g.out[0] = h->ws_h; g.out_split = D;
+      if ((rc = gemm(h, g, s))) return rc;
+    }
+    {  // hid = relu(LN2(h) W1^T + b1)          (transformer.py:370-372)
+      GemmArgs g = {};
+      g.A = h->ws_h; g.W = w + lo.w1; g.bias = w + lo.b1;
+      g.M = M; g.N = DFF; g.K = D; g.ln_g = w + lo.ln2_g; g.ln_b = w + lo.ln2_b; g.relu = 1;
+      g.out[0] = h->ws_hid; g.out_split = DFF;
+      if ((rc = gemm(h, g, s))) return rc;
+    }
+    {  // h += hid W2^T + b2                    (transformer.py:374, :237)
+      GemmArgs g = {};
+      g.A = h->ws_hid; g.W = w + lo.w2; g.bias = w + lo.b2;
+      g.M = M; g.N = D; g.K = DFF; g.residual = h->ws_h;
+      g.out[0] = h->ws_h; g.out_split = D;
+      if ((rc = gemm(h, g, s))) return rc;
+    }
+  }
+  cudaError_t e = launch_classifier(h->ws_h, w + h->lay.lnf_g, w + h->lay.lnf_b, w + h->lay.wc,
+                                    w + h->lay.bc, M, prob, logp, s);
+  if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("classifier: ") + cudaGetErrorString(e));
+  h->launches++;
+  return VADB_OK;
+}
+
+int check_ready(vadb_handle* h) {
+  if (!h) return VADB_E_INVALID;
+  if (!h->loaded) return fail(h, VADB_E_STATE, "weights not loaded (call vadb_load_weights first)");
+  return VADB_OK;
+}
+
+int window_W(int half, int jump) { return 2 * (half - 1) / jump + 3; }
+
+int ensure_bytes(vadb_handle* h, void** p, size_t* have, size_t need, bool pinned) {
+  if (need <= *have) return VADB_OK;
+  if (*p) {
+    cudaDeviceSynchronize();   // the old buffer may still be referenced by queued work
+    if (pinned) cudaFreeHost(*p); else cudaFree(*p);
+    *p = nullptr; *have = 0;
+  }
+  size_t n = need + need / 4;
+  if (pinned) CU_TRY(h, cudaMallocHost(p, n)); else CU_TRY(h, cudaMalloc(p, n));
+  *have = n;
+  return VADB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vadb_version(void) { return "vadb200 0.1 sm_100a"; }
+
+size_t vadb_weight_count(const vadb_config* cfg) {
+  if (!cfg || cfg->feature_size <= 0 || cfg->num_layers <= 0) return 0;
+  return make_layout(cfg->feature_size, cfg->num_layers).total;
+}
+
+const char* vadb_last_error(const vadb_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int64_t vadb_launch_count(const vadb_handle* h) { return h ? h->launches : 0; }
+
+int vadb_create(vadb_handle** out, const vadb_config* cfg, int device) {
+  if (!out || !cfg) return fail(nullptr, VADB_E_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->d_model != D) return fail(nullptr, VADB_E_INVALID, "d_model must be 128 (kernels are specialised)");
+  if (cfg->feature_size <= 0 || cfg->feature_size > 4096) return fail(nullptr, VADB_E_INVALID, "bad feature_size");
+  if (cfg->num_layers <= 0 || cfg->num_layers > 64) return fail(nullptr, VADB_E_INVALID, "bad num_layers");
+  if (cfg->compute_dtype != VADB_F32 && cfg->compute_dtype != VADB_BF16)
+    return fail(nullptr, VADB_E_INVALID, "compute_dtype must be VADB_F32 or VADB_BF16");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, VADB_E_CUDA, std::string("no CUDA device (there is no CPU fallback): ") +
+                                          cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, VADB_E_INVALID, "bad device index");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, VADB_E_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, VADB_E_INVALID, "libvadb200 is built for sm_100a (B200) only");
+  vadb_handle* h = new (std::nothrow) vadb_handle();
+  if (!h) return fail(nullptr, VADB_E_NOMEM, "out of host memory");
+  h->cfg = *cfg;
+  h->device = device;
+  h->lay = make_layout(cfg->feature_size, cfg->num_layers);
+  DeviceGuard dg(device);
+  e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete h; return fail(nullptr, VADB_E_CUDA, m); }
+  *out = h;
+  return VADB_OK;
+}
+
+void vadb_destroy(vadb_handle* h) {
+  if (!h) return;
+  DeviceGuard dg(h->device);
+  cudaDeviceSynchronize();
+  free_dev(h->w32); free_dev(h->wqkv); free_dev(h->bqkv);
+  free_dev(h->wqkv_bf); free_dev(h->wo_bf); free_dev(h->w1_bf); free_dev(h->w2_bf);
+  free_dev(h->pe);
+  free_dev(h->ws_h); free_dev(h->ws_q); free_dev(h->ws_k); free_dev(h->ws_v); free_dev(h->ws_o);
+  free_dev(h->ws_hid); free_dev(h->ws_prob);
+  if (h->pin_in) cudaFreeHost(h->pin_in);
+  if (h->pin_out) cudaFreeHost(h->pin_out);
+  if (h->dev_in) cudaFree(h->dev_in);
+  if (h->dev_out) cudaFree(h->dev_out);
+  if (h->dev_len) cudaFree(h->dev_len);
+  if (h->win_prob) cudaFree(h->win_prob);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int vadb_load_weights(vadb_handle* h, const float* blob, size_t count, int on_device, void* stream) {
+  if (!h || !blob) return VADB_E_INVALID;
+  if (count != h->lay.total) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "weight blob has %zu floats, config needs %zu", count, h->lay.total);
+    return fail(h, VADB_E_INVALID, buf);
+  }
+  DeviceGuard dg(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int L = h->cfg.num_layers;
+  if (!h->w32) {
+    CU_TRY(h, cudaMalloc(&h->w32, count * sizeof(float)));
+    CU_TRY(h, cudaMalloc(&h->wqkv, (size_t)L * 3 * D * D * sizeof(float)));
+    CU_TRY(h, cudaMalloc(&h->bqkv, (size_t)L * 3 * D * sizeof(float)));
+    CU_TRY(h, cudaMalloc(&h->wqkv_bf, (size_t)L * 3 * D * D * sizeof(bf16)));
+    CU_TRY(h, cudaMalloc(&h->wo_bf, (size_t)L * D * D * sizeof(bf16)));
+    CU_TRY(h, cudaMalloc(&h->w1_bf, (size_t)L * DFF * D * sizeof(bf16)));
+    CU_TRY(h, cudaMalloc(&h->w2_bf, (size_t)L * D * DFF * sizeof(bf16)));
+  }
+  CU_TRY(h, cudaMemcpyAsync(h->w32, blob, count * sizeof(float),
+                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  for (int l = 0; l < L; ++l) {
+    const LayerOffsets& lo = h->lay.layers[l];
+    const size_t srcw[3] = {lo.wq, lo.wk, lo.wv}, srcb[3] = {lo.bq, lo.bk, lo.bv};
+    for (int j = 0; j < 3; ++j) {
+      CU_TRY(h, cudaMemcpyAsync(h->wqkv + ((size_t)l * 3 + j) * D * D, h->w32 + srcw[j],
+                                (size_t)D * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      CU_TRY(h, cudaMemcpyAsync(h->bqkv + ((size_t)l * 3 + j) * D, h->w32 + srcb[j],
+                                (size_t)D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    CU_TRY(h, launch_f32_to_bf16(h->wqkv + (size_t)l * 3 * D * D, h->wqkv_bf + (size_t)l * 3 * D * D,
+                                 (size_t)3 * D * D, s));
+    CU_TRY(h, launch_f32_to_bf16(h->w32 + lo.wo, h->wo_bf + (size_t)l * D * D, (size_t)D * D, s));
+    CU_TRY(h, launch_f32_to_bf16(h->w32 + lo.w1, h->w1_bf + (size_t)l * DFF * D, (size_t)DFF * D, s));
+    CU_TRY(h, launch_f32_to_bf16(h->w32 + lo.w2, h->w2_bf + (size_t)l * D * DFF, (size_t)D * DFF, s));
+  }
+  CU_TRY(h, cudaStreamSynchronize(s));
+  h->loaded = true;
+  return VADB_OK;
+}
+
+int vadb_reserve(vadb_handle* h, int B, int T) {
+  if (!h || B <= 0 || T <= 0) return VADB_E_INVALID;
+  DeviceGuard dg(h->device);
+  int rc = ensure_pe(h, T);
+  if (rc) return rc;
+  return ensure_workspace(h, (size_t)clips_per_pass(B, T) * T);
+}
+
+int vadb_positional_table(vadb_handle* h, int T, float* out_host) {
+  if (!h || T <= 0 || !out_host) return VADB_E_INVALID;
+  DeviceGuard dg(h->device);
+  int rc = ensure_pe(h, T);
+  if (rc) return rc;
+  CU_TRY(h, cudaMemcpy(out_host, h->pe, (size_t)T * D * sizeof(float), cudaMemcpyDeviceToHost));
+  return VADB_OK;
+}
+
+int vadb_forward(vadb_handle* h, const void* x, int x_dtype, const int32_t* lengths, int B, int T,
+                 float* prob, float* logp, void* stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!x || B < 0 || T < 0) return fail(h, VADB_E_INVALID, "bad forward arguments");
+  if (x_dtype != VADB_F32 && x_dtype != VADB_BF16) return fail(h, VADB_E_INVALID, "x_dtype must be f32 or bf16");
+  if (B == 0 || T == 0) return VADB_OK;
+  DeviceGuard dg(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = ensure_pe(h, T))) return rc;
+  const int cpp = clips_per_pass(B, T);
+  if ((rc = ensure_workspace(h, (size_t)cpp * T))) return rc;
+  const int F = h->cfg.feature_size;
+  const size_t xsz = x_dtype == VADB_BF16 ? 2 : 4;
+  for (int b0 = 0; b0 < B; b0 += cpp) {
+    const int Bc = std::min(cpp, B - b0);
+    // h = x W_in^T + b_in + PE[:T]/sqrt(d)     (self_attention.py:13-14, transformer.py:401)
+    GemmArgs g = {};
+    g.A = (const char*)x + (size_t)b0 * T * F * xsz; g.a_is_bf16 = x_dtype == VADB_BF16;
+    g.W = h->w32 + h->lay.w_in; g.bias = h->w32 + h->lay.b_in;
+    g.M = Bc * T; g.N = D; g.K = F; g.pe = h->pe; g.pe_T = T;
+    g.out[0] = h->ws_h; g.out_split = D;
+    if ((rc = gemm(h, g, s))) return rc;
+    if ((rc = run_encoder(h, lengths ? lengths + b0 : nullptr, Bc, T,
+                          prob ? prob + (size_t)b0 * T : nullptr,
+                          logp ? logp + (size_t)b0 * T * 2 : nullptr, s)))
+      return rc;
+  }
+  return VADB_OK;
+}
+
+int vadb_forward_host(vadb_handle* h, const float* x, const int32_t* lengths, int B, int T,
+                      float* prob, float* logp) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!x || B < 0 || T < 0) return fail(h, VADB_E_INVALID, "bad forward arguments");
+  if (B == 0 || T == 0) return VADB_OK;
+  DeviceGuard dg(h->device);
+  cudaStream_t s = h->own_stream;
+  const int F = h->cfg.feature_size;
+  const size_t n = (size_t)B * T;
+  const size_t in_bytes = n * F * sizeof(float);
+  const size_t out_bytes = n * 3 * sizeof(float);      // prob [n] + logp [2n]
+  if ((rc = ensure_bytes(h, &h->pin_in, &h->pin_in_bytes, in_bytes, true))) return rc;
+  if ((rc = ensure_bytes(h, &h->pin_out, &h->pin_out_bytes, out_bytes, true))) return rc;
+  if ((rc = ensure_bytes(h, &h->dev_in, &h->dev_in_bytes, in_bytes, false))) return rc;
+  if ((rc = ensure_bytes(h, &h->dev_out, &h->dev_out_bytes, out_bytes, false))) return rc;
+  int32_t* dlen = nullptr;
+  if (lengths) {
+    if ((size_t)B > h->dev_len_n) {
+      if (h->dev_len) cudaFree(h->dev_len);
+      h->dev_len = nullptr; h->dev_len_n = 0;
+      CU_TRY(h, cudaMalloc(&h->dev_len, (size_t)B * sizeof(int32_t)));
+      h->dev_len_n = B;
+    }
+    CU_TRY(h, cudaMemcpyAsync(h->dev_len, lengths, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    dlen = h->dev_len;
+  }
+  memcpy(h->pin_in, x, in_bytes);
+  CU_TRY(h, cudaMemcpyAsync(h->dev_in, h->pin_in, in_bytes, cudaMemcpyHostToDevice, s));
+  float* dprob = (float*)h->dev_out;
+  float* dlogp = dprob + n;
+  if ((rc = vadb_forward(h, h->dev_in, VADB_F32, dlen, B, T, prob ? dprob : nullptr,
+                         logp ? dlogp : nullptr, s)))
+    return rc;
+  if (prob) CU_TRY(h, cudaMemcpyAsync(h->pin_out, dprob, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (logp) CU_TRY(h, cudaMemcpyAsync((float*)h->pin_out + n, dlogp, 2 * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CU_TRY(h, cudaStreamSynchronize(s));
+  if (prob) memcpy(prob, h->pin_out, n * sizeof(float));
+  if (logp) memcpy(logp, (float*)h->pin_out + n, 2 * n * sizeof(float));
+  return VADB_OK;
+}
+
+int vadb_predict_probabilities(vadb_handle* h, const float* feat, int L, int half, int jump,
+                               float* probs_LW, float* mean_L, void* stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!feat || L < 0 || half < 1 || jump < 1) return fail(h, VADB_E_INVALID, "bad window arguments");
+  const int W = window_W(half, jump);
+  const int nl = (half + jump - 1) / jump;
+  if (2 * nl + 1 != W)   // the reference's scatter (vad/predictor.py:254) has mismatching shapes here
+    return fail(h, VADB_E_INVALID, "context_window half/jump inconsistent with 2*(half-1)//jump+3 window slots");
+  if (L == 0) return VADB_OK;
+  DeviceGuard dg(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = L - 2 * half;                         // vad/predictor.py:169
+  const int F = h->cfg.feature_size;
+  if (n > 0) {
+    if ((rc = ensure_pe(h, W))) return rc;
+    const int wpp = clips_per_pass(n, W);             // windows per pass
+    // per-window probabilities for all n windows live in one [n, W] buffer
+    if ((rc = ensure_workspace(h, (size_t)wpp * W))) return rc;
+    float* prob_all = nullptr;
+    size_t need = (size_t)n * W * sizeof(float);
+    if ((rc = ensure_bytes(h, &h->win_prob, &h->win_prob_bytes, need, false))) return rc;
+    prob_all = (float*)h->win_prob;
+    for (int c0 = 0; c0 < n; c0 += wpp) {
+      const int nc = std::min(wpp, n - c0);
+      // window gather folded into the front-end GEMM's A-row index (vad/predictor.py:182-218);
+      // the positional slot of row m is m % W (the window is the model's whole sequence)
+      GemmArgs g = {};
+      g.A = feat + (size_t)c0 * F; g.W = h->w32 + h->lay.w_in; g.bias = h->w32 + h->lay.b_in;
+      g.M = nc * W; g.N = D; g.K = F; g.pe = h->pe; g.pe_T = W;
+      g.win_W = W; g.win_half = half; g.win_jump = jump;
+      g.out[0] = h->ws_h; g.out_split = D;
+      if ((rc = gemm(h, g, s))) return rc;
+      if ((rc = run_encoder(h, nullptr, nc, W, prob_all + (size_t)c0 * W, nullptr, s))) return rc;
+    }
+    cudaError_t e = launch_boost(prob_all, L, half, jump, W, probs_LW, mean_L, s);
+    if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("boost: ") + cudaGetErrorString(e));
+  } else {
+    cudaError_t e = launch_boost(nullptr, L, half, jump, W, probs_LW, mean_L, s);
+    if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("boost: ") + cudaGetErrorString(e));
+  }
+  h->launches++;
+  return VADB_OK;
+}
+
+int vadb_predict_probabilities_host(vadb_handle* h, const float* feat, int L, int half, int jump,
+                                    float* probs_LW, float* mean_L) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!feat || L < 0 || half < 1 || jump < 1) return fail(h, VADB_E_INVALID, "bad window arguments");
+  if (L == 0) return VADB_OK;
+  DeviceGuard dg(h->device);
+  cudaStream_t s = h->own_stream;
+  const int W = window_W(half, jump);
+  const int F = h->cfg.feature_size;
+  const size_t in_bytes = (size_t)L * F * sizeof(float);
+  const size_t out_floats = (size_t)L * (W + 1);
+  if ((rc = ensure_bytes(h, &h->pin_in, &h->pin_in_bytes, in_bytes, true))) return rc;
+  if ((rc = ensure_bytes(h, &h->pin_out, &h->pin_out_bytes, out_floats * sizeof(float), true))) return rc;
+  if ((rc = ensure_bytes(h, &h->dev_in, &h->dev_in_bytes, in_bytes + out_floats * sizeof(float), false))) return rc;
+  memcpy(h->pin_in, feat, in_bytes);
+  CU_TRY(h, cudaMemcpyAsync(h->dev_in, h->pin_in, in_bytes, cudaMemcpyHostToDevice, s));
+  float* d_lw = (float*)((char*)h->dev_in + in_bytes);
+  float* d_mean = d_lw + (size_t)L * W;
+  if ((rc = vadb_predict_probabilities(h, (const float*)h->dev_in, L, half, jump, d_lw, d_mean, s))) return rc;
+  CU_TRY(h, cudaMemcpyAsync(h->pin_out, d_lw, out_floats * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CU_TRY(h, cudaStreamSynchronize(s));
+  if (probs_LW) memcpy(probs_LW, h->pin_out, (size_t)L * W * sizeof(float));
+  if (mean_L) memcpy(mean_L, (float*)h->pin_out + (size_t)L * W, (size_t)L * sizeof(float));
+  return VADB_OK;
+}
+
+int vadb_attention(vadb_handle* h, const void* q, const void* k, const void* v, void* o, int dtype,
+                   const int32_t* lengths, int B, int T, void* stream) {
+  if (!h || !q || !k || !v || !o || B < 0 || T < 0) return VADB_E_INVALID;
+  if (dtype != VADB_F32 && dtype != VADB_BF16) return fail(h, VADB_E_INVALID, "dtype must be f32 or bf16");
+  if (B == 0 || T == 0) return VADB_OK;
+  DeviceGuard dg(h->device);
+  return attention(h, q, k, v, o, dtype, lengths, B, T, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// Shared declarations for libvadb200 (B200 / sm_100a Self-Attentive VAD forward path).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/vadb200.h"
+
+namespace vadb {
+
+constexpr int D = 128;       // d_model == d_head (n_heads = 1): vad/models/self_attention.py:17-19
+constexpr int DFF = 512;     // d_ff = 4*d_model: vad/models/self_attention.py:10
+constexpr float LN_EPS = 1e-5f;
+
+typedef __nv_bfloat16 bf16;
+
+// Offsets (in floats) of every tensor inside the packed fp32 blob; order == state_dict order.
+struct LayerOffsets {
+  size_t wq, bq, wk, bk, wv, bv, wo, bo, ln1_g, ln1_b, w1, b1, w2, b2, ln2_g, ln2_b;
+};
+struct BlobLayout {
+  size_t w_in, b_in;
+  std::vector<LayerOffsets> layers;
+  size_t lnf_g, lnf_b, wc, bc, total;
+};
+BlobLayout make_layout(int F, int L);
+
+// ---------------------------------------------------------------------------------------
+// generic fp32 CUDA-core GEMM with fused prologue/epilogue (k_gemm_f32.cu)
+//   C[m, n] = epi( sum_k pro(A)[m, k] * W[n, k] + bias[n] )
+// ---------------------------------------------------------------------------------------
+struct GemmArgs {
+  const void* A;          // [M, K] row-major, fp32 or bf16
+  int a_is_bf16;
+  const float* W;         // [N, K] row-major (nn.Linear layout)
+  const float* bias;      // [N]
+  int M, N, K;
+  // prologue: LayerNorm over K (requires K == 128)
+  const float* ln_g;      // nullptr -> no LayerNorm
+  const float* ln_b;
+  // epilogue
+  int relu;
+  const float* residual;  // [M, N] fp32 or nullptr (may alias out[0])
+  const float* pe;        // [T, N] already divided by sqrt(d), or nullptr
+  int pe_T;               // row m uses pe[m % pe_T]
+  // window gather (vad/predictor.py:182-218) folded into the A-row index: when win_W > 0,
+  // output row m = i*win_W + k reads A row  half + i + rel[k]
+  int win_W, win_half, win_jump;
+  // outputs: columns [j*out_split, (j+1)*out_split) go to out[j] (row stride out_split)
+  void* out[3];
+  int out_split;          // == N when a single output
+  int out_is_bf16;
+};
+cudaError_t launch_gemm_f32(const GemmArgs& a, cudaStream_t s);
+
+// fp32 flash attention on CUDA cores (k_attn_f32.cu)
+cudaError_t launch_attn_f32(const float* q, const float* k, const float* v, float* o,
+                            const int32_t* lengths, int B, int T, cudaStream_t s);
+
+// bf16 tcgen05 attention (k_attn_tc.cu)
+cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o,
+                           const int32_t* lengths, int B, int T, cudaStream_t s,
+                           std::string* err);
+
+// final LayerNorm + classifier + sigmoid/log-softmax (k_classifier.cu)
+cudaError_t launch_classifier(const float* h, const float* g, const float* b, const float* wc,
+                              const float* bc, int M, float* prob, float* logp, cudaStream_t s);
+
+// window path helpers (k_window.cu)
+cudaError_t launch_boost(const float* prob_nW, int L, int half, int jump, int W,
+                         float* probs_LW, float* mean_L, cudaStream_t s);
+
+// misc element-wise (k_window.cu)
+cudaError_t launch_f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t s);
+
+}  // namespace vadb

@@ -1,0 +1,223 @@
+"""VadEngine: one libvadb200 handle on one GPU; torch tensors in, torch tensors out.
+
+PyTorch is plumbing here (device memory, streams); every FLOP of the forward pass runs in the
+hand-written sm_100a kernels behind the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+def state_dict_keys(num_layers: int):
+    """Reference state_dict order (vad/models/self_attention.py:12-21; names in SURVEY.md 8 a1)."""
+    keys = ["input_layer.0.weight", "input_layer.0.bias"]
+    for l in range(num_layers):
+        p = f"encoder.layers.{l}."
+        for proj in ("query", "key", "value", "final"):
+            keys += [p + f"self_attention.{proj}_projection.weight",
+                     p + f"self_attention.{proj}_projection.bias"]
+        keys += [p + "self_attention_sublayer.layer_norm.weight",
+                 p + "self_attention_sublayer.layer_norm.bias",
+                 p + "feed_forward.feed_forward.0.weight", p + "feed_forward.feed_forward.0.bias",
+                 p + "feed_forward.feed_forward.3.weight", p + "feed_forward.feed_forward.3.bias",
+                 p + "feed_forward_sublayer.layer_norm.weight",
+                 p + "feed_forward_sublayer.layer_norm.bias"]
+    keys += ["encoder.layer_norm.weight", "encoder.layer_norm.bias",
+             "classifier.weight", "classifier.bias"]
+    return keys
+
+
+def infer_config(state: Dict[str, torch.Tensor]):
+    d_model, feature_size = state["input_layer.0.weight"].shape
+    L = 0
+    while f"encoder.layers.{L}.self_attention.query_projection.weight" in state:
+        L += 1
+    return int(feature_size), L, int(d_model)
+
+
+def pack_state(state: Dict[str, torch.Tensor], num_layers: int) -> torch.Tensor:
+    """Flatten a reference state_dict into the packed fp32 blob vadb_load_weights takes."""
+    parts = [state[k].detach().to(torch.float32).reshape(-1).cpu() for k in state_dict_keys(num_layers)]
+    return torch.cat(parts).contiguous()
+
+
+_DTYPES = {"fp32": _cabi.VADB_F32, "f32": _cabi.VADB_F32, "float32": _cabi.VADB_F32,
+           "bf16": _cabi.VADB_BF16, "bfloat16": _cabi.VADB_BF16}
+
+
+class VadEngine:
+    """Owns a vadb_handle.  ``compute_dtype``: "fp32" (<=1e-3 parity path) or "bf16"."""
+
+    def __init__(self, feature_size: int, num_layers: int, d_model: int = 128,
+                 compute_dtype: str = "bf16", device: Optional[torch.device] = None):
+        self._lib = _cabi.load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("vad_b200 needs a CUDA device (B200); there is no CPU fallback")
+        device = torch.device(device if device is not None else "cuda")
+        if device.type != "cuda":
+            raise RuntimeError(f"vad_b200 runs on CUDA devices only, got {device}")
+        self.device = torch.device("cuda", device.index if device.index is not None
+                                   else torch.cuda.current_device())
+        self.feature_size, self.num_layers, self.d_model = feature_size, num_layers, d_model
+        self.compute_dtype = compute_dtype
+        self._cfg = _cabi.VadbConfig(feature_size, num_layers, d_model, _DTYPES[compute_dtype])
+        self._h = C.c_void_p()
+        rc = self._lib.vadb_create(C.byref(self._h), C.byref(self._cfg), self.device.index)
+        _cabi.check(self._lib, None, rc, "vadb_create")
+        self.weight_count = int(self._lib.vadb_weight_count(C.byref(self._cfg)))
+
+    # -- lifecycle ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.vadb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @classmethod
+    def from_state_dict(cls, state, compute_dtype="bf16", device=None):
+        F_, L, d = infer_config(state)
+        eng = cls(F_, L, d, compute_dtype, device)
+        eng.load_state_dict(state)
+        return eng
+
+    def load_state_dict(self, state):
+        self.load_blob(pack_state(state, self.num_layers))
+
+    def load_blob(self, blob: torch.Tensor):
+        """blob: packed fp32 weights, on the host or already on this device (e.g. the buffer a
+        rank received from the one-off NCCL broadcast)."""
+        assert blob.dtype == torch.float32 and blob.is_contiguous()
+        on_dev = blob.is_cuda
+        if on_dev:
+            assert blob.device == self.device
+        rc = self._lib.vadb_load_weights(self._h, C.c_void_p(blob.data_ptr()), blob.numel(),
+                                         1 if on_dev else 0, self._stream_ptr())
+        _cabi.check(self._lib, self._h, rc, "vadb_load_weights")
+
+    def _stream_ptr(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reserve(self, B: int, T: int):
+        _cabi.check(self._lib, self._h, self._lib.vadb_reserve(self._h, B, T), "vadb_reserve")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.vadb_launch_count(self._h))
+
+    # -- hot path ----------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None,
+                want_logp: bool = True, want_prob: bool = True):
+        """x [B,T,F] fp32/bf16.  CUDA tensor -> async on the current stream, returns CUDA
+        tensors; CPU tensor -> end-to-end host call (H2D, forward, D2H), returns CPU tensors.
+        Returns (prob [B,T] fp32 or None, logp [B,T,2] fp32 or None)."""
+        if x.dim() != 3 or x.shape[2] != self.feature_size:
+            raise ValueError(f"expected [B,T,{self.feature_size}] features, got {tuple(x.shape)}")
+        B, T, _ = x.shape
+        if lengths is not None:
+            if lengths.numel() != B:
+                raise ValueError("lengths must have one entry per clip")
+        if not x.is_cuda:
+            return self._forward_host(x, lengths, want_logp, want_prob)
+        if x.device != self.device:
+            raise ValueError(f"features on {x.device}, engine on {self.device}")
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.to(torch.float32)
+        x = x.contiguous()
+        ln_ptr = None
+        if lengths is not None:
+            lengths = lengths.to(device=self.device, dtype=torch.int32).contiguous()
+            ln_ptr = C.c_void_p(lengths.data_ptr())
+        prob = torch.empty((B, T), dtype=torch.float32, device=self.device) if want_prob else None
+        logp = torch.empty((B, T, 2), dtype=torch.float32, device=self.device) if want_logp else None
+        with torch.cuda.device(self.device):
+            rc = self._lib.vadb_forward(
+                self._h, C.c_void_p(x.data_ptr()),
+                _cabi.VADB_BF16 if x.dtype == torch.bfloat16 else _cabi.VADB_F32, ln_ptr, B, T,
+                C.c_void_p(prob.data_ptr()) if want_prob and prob.numel() else None,
+                C.c_void_p(logp.data_ptr()) if want_logp and logp.numel() else None,
+                self._stream_ptr())
+        _cabi.check(self._lib, self._h, rc, "vadb_forward")
+        return prob, logp
+
+    def _forward_host(self, x, lengths, want_logp, want_prob):
+        B, T, _ = x.shape
+        x = x.to(torch.float32).contiguous()
+        prob = torch.empty((B, T), dtype=torch.float32) if want_prob else None
+        logp = torch.empty((B, T, 2), dtype=torch.float32) if want_logp else None
+        ln_ptr = None
+        if lengths is not None:
+            lengths = lengths.to(device="cpu", dtype=torch.int32).contiguous()
+            ln_ptr = C.c_void_p(lengths.data_ptr())
+        rc = self._lib.vadb_forward_host(
+            self._h, C.c_void_p(x.data_ptr()), ln_ptr, B, T,
+            C.c_void_p(prob.data_ptr()) if want_prob and prob.numel() else None,
+            C.c_void_p(logp.data_ptr()) if want_logp and logp.numel() else None)
+        _cabi.check(self._lib, self._h, rc, "vadb_forward_host")
+        return prob, logp
+
+    def predict_probabilities(self, feature, half: int, jump: int):
+        """feature [L,F] (numpy / CPU tensor -> host call; CUDA tensor -> device call).
+        Returns (probs [L,W], mean [L]) as numpy arrays (host) or CUDA tensors (device)."""
+        W = 2 * (half - 1) // jump + 3
+        if isinstance(feature, torch.Tensor) and feature.is_cuda:
+            feat = feature.to(torch.float32).contiguous()
+            L = feat.shape[0]
+            probs = torch.empty((L, W), dtype=torch.float32, device=self.device)
+            mean = torch.empty((L,), dtype=torch.float32, device=self.device)
+            with torch.cuda.device(self.device):
+                rc = self._lib.vadb_predict_probabilities(
+                    self._h, C.c_void_p(feat.data_ptr()), L, half, jump,
+                    C.c_void_p(probs.data_ptr()) if L else None,
+                    C.c_void_p(mean.data_ptr()) if L else None, self._stream_ptr())
+            _cabi.check(self._lib, self._h, rc, "vadb_predict_probabilities")
+            return probs, mean
+        feat = np.ascontiguousarray(np.asarray(feature, dtype=np.float32))
+        if feat.ndim != 2 or feat.shape[1] != self.feature_size:
+            raise ValueError(f"expected [L,{self.feature_size}] features, got {feat.shape}")
+        L = feat.shape[0]
+        probs = np.empty((L, W), dtype=np.float32)
+        mean = np.empty((L,), dtype=np.float32)
+        rc = self._lib.vadb_predict_probabilities_host(
+            self._h, feat.ctypes.data_as(C.c_void_p), L, half, jump,
+            probs.ctypes.data_as(C.c_void_p), mean.ctypes.data_as(C.c_void_p))
+        _cabi.check(self._lib, self._h, rc, "vadb_predict_probabilities_host")
+        return probs, mean
+
+    def attention(self, q, k, v, lengths=None):
+        """Stage-level entry (kernel parity tests / roofline bench): q,k,v [B,T,128] CUDA,
+        fp32 -> CUDA-core kernel, bf16 -> tcgen05 kernel."""
+        assert q.is_cuda and q.shape == k.shape == v.shape and q.shape[-1] == 128
+        assert q.dtype == k.dtype == v.dtype and q.dtype in (torch.float32, torch.bfloat16)
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        B, T, _ = q.shape
+        o = torch.empty_like(q)
+        ln_ptr = None
+        if lengths is not None:
+            lengths = lengths.to(device=self.device, dtype=torch.int32).contiguous()
+            ln_ptr = C.c_void_p(lengths.data_ptr())
+        with torch.cuda.device(self.device):
+            rc = self._lib.vadb_attention(
+                self._h, C.c_void_p(q.data_ptr()), C.c_void_p(k.data_ptr()),
+                C.c_void_p(v.data_ptr()), C.c_void_p(o.data_ptr()),
+                _cabi.VADB_BF16 if q.dtype == torch.bfloat16 else _cabi.VADB_F32, ln_ptr, B, T,
+                self._stream_ptr())
+        _cabi.check(self._lib, self._h, rc, "vadb_attention")
+        return o
+
+    def positional_table(self, T: int) -> np.ndarray:
+        out = np.empty((T, 128), dtype=np.float32)
+        rc = self._lib.vadb_positional_table(self._h, T, out.ctypes.data_as(C.c_void_p))
+        _cabi.check(self._lib, self._h, rc, "vadb_positional_table")
+        return out
