@@ -202,17 +202,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       tmem_ld32(ts + 32, sv[1]);
       tmem_ld_wait();
       const int kbase = j * BKV;
-      const bool partial = kbase + BKV > len;      // only the last tile can hold masked keys
-      float mx = -CUDART_INF_F;
+      if (kbase + BKV > len) {                     // warp-uniform: only the last tile holds masked keys
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2)
+        for (int h2 = 0; h2 < 2; ++h2)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float v = __uint_as_float(sv[h2][i]);
-          if (partial && kbase + h2 * 32 + i >= len) v = -CUDART_INF_F;
-          sv[h2][i] = __float_as_uint(v);
-          mx = fmaxf(mx, v);
-        }
+          for (int i = 0; i < 32; ++i)
+            if (kbase + h2 * 32 + i >= len) sv[h2][i] = 0xFF800000u;   // -inf
+      }
+      // row max with 4 independent chains (ILP: one thread owns the whole row)
+      float mx4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(sv[0][i]), __uint_as_float(sv[0][i + 1])));
+        mx4[((i >> 1) + 2) & 3] = fmaxf(mx4[((i >> 1) + 2) & 3], fmaxf(__uint_as_float(sv[1][i]), __uint_as_float(sv[1][i + 1])));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float mxl = mx * c;
       if (j == 0) {
         m_ref = mxl;
@@ -239,7 +243,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         }
       }
       const float m_use = (m_ref == -CUDART_INF_F) ? 0.f : m_ref;
-      float psum = 0.f;
+      float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {             // 8 chunks of 8 keys = 16 bytes of bf16 each
         uint32_t pk[4];
@@ -248,11 +252,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           const int i0 = ch * 8 + e * 2;
           const float p0 = fast_exp2(fmaf(__uint_as_float(sv[i0 >> 5][i0 & 31]), c, -m_use));
           const float p1 = fast_exp2(fmaf(__uint_as_float(sv[(i0 + 1) >> 5][(i0 + 1) & 31]), c, -m_use));
-          psum += p0 + p1;
+          ps4[e] += p0 + p1;
           pk[e] = pack_bf16(p0, p1);
         }
         *reinterpret_cast<uint4*>(p_row + sw128_offset(row, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
+      const float psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
       l_sum += psum;
       fence_proxy_async_smem();     // generic-proxy P writes -> visible to the tensor core (async proxy)
       tc_fence_before();

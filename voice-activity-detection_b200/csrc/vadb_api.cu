@@ -59,12 +59,13 @@ struct vadb_handle {
 
   float* pe = nullptr;       // [pe_T, 128] = PE / sqrt(d)
   int pe_T = 0;
+  int num_sms = 148;
 
   // workspace, sized in frames
   size_t cap_frames = 0;
   float* ws_h = nullptr;
   void* ws_q = nullptr; void* ws_k = nullptr; void* ws_v = nullptr; void* ws_o = nullptr;
-  float* ws_hid = nullptr;
+  void* ws_hid = nullptr;
   float* ws_prob = nullptr;
 
   // host-call staging
@@ -144,7 +145,7 @@ int ensure_workspace(vadb_handle* h, size_t frames) {
   CU_TRY(h, cudaMalloc(&h->ws_k, cap * D * act));
   CU_TRY(h, cudaMalloc(&h->ws_v, cap * D * act));
   CU_TRY(h, cudaMalloc(&h->ws_o, cap * D * act));
-  CU_TRY(h, cudaMalloc(&h->ws_hid, cap * DFF * sizeof(float)));
+  CU_TRY(h, cudaMalloc(&h->ws_hid, cap * DFF * act));
   CU_TRY(h, cudaMalloc(&h->ws_prob, cap * sizeof(float)));
   h->cap_frames = cap;
   return VADB_OK;
@@ -160,6 +161,14 @@ int clips_per_pass(int B, int T) {
 int gemm(vadb_handle* h, const GemmArgs& a, cudaStream_t s) {
   cudaError_t e = launch_gemm_f32(a, s);
   if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("gemm_f32: ") + cudaGetErrorString(e));
+  h->launches++;
+  return VADB_OK;
+}
+
+int gemm_tc(vadb_handle* h, const GemmTcArgs& a, cudaStream_t s) {
+  std::string err;
+  cudaError_t e = launch_gemm_tc(a, h->num_sms, s, &err);
+  if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("gemm_tc: ") + cudaGetErrorString(e) + " " + err);
   h->launches++;
   return VADB_OK;
 }
@@ -190,21 +199,53 @@ int run_encoder(vadb_handle* h, const int32_t* lengths, int Bc, int T, float* pr
   for (int l = 0; l < h->cfg.num_layers; ++l) {
     const LayerOffsets& lo = h->lay.layers[l];
     int rc;
+    if (bf) {
+      // bf16 mode: every Linear on the tensor cores (k_gemm_tc.cu), attention in k_attn_tc.cu
+      {  // a = LN1(h); q,k,v = a W^T + b        (transformer.py:235-236, :281-284)
+        GemmTcArgs g = {};
+        g.M = M; g.N = 3 * D; g.K = D; g.w_bf16 = h->wqkv_bf + (size_t)l * 3 * D * D;
+        g.a_f32 = h->ws_h; g.ln_g = w + lo.ln1_g; g.ln_b = w + lo.ln1_b;
+        g.bias = h->bqkv + (size_t)l * 3 * D;
+        g.out[0] = h->ws_q; g.out[1] = h->ws_k; g.out[2] = h->ws_v;
+        if ((rc = gemm_tc(h, g, s))) return rc;
+      }
+      if ((rc = attention(h, h->ws_q, h->ws_k, h->ws_v, h->ws_o, VADB_BF16, lengths, Bc, T, s))) return rc;
+      {  // h += o Wo^T + bo                      (transformer.py:347, :237)
+        GemmTcArgs g = {};
+        g.M = M; g.N = D; g.K = D; g.w_bf16 = h->wo_bf + (size_t)l * D * D;
+        g.a_bf16 = (const bf16*)h->ws_o; g.bias = w + lo.bo; g.residual = h->ws_h;
+        g.out_f32 = 1; g.out[0] = h->ws_h;
+        if ((rc = gemm_tc(h, g, s))) return rc;
+      }
+      {  // hid = relu(LN2(h) W1^T + b1)          (transformer.py:370-372)
+        GemmTcArgs g = {};
+        g.M = M; g.N = DFF; g.K = D; g.w_bf16 = h->w1_bf + (size_t)l * DFF * D;
+        g.a_f32 = h->ws_h; g.ln_g = w + lo.ln2_g; g.ln_b = w + lo.ln2_b;
+        g.bias = w + lo.b1; g.relu = 1; g.out[0] = h->ws_hid;
+        if ((rc = gemm_tc(h, g, s))) return rc;
+      }
+      {  // h += hid W2^T + b2                    (transformer.py:374, :237)
+        GemmTcArgs g = {};
+        g.M = M; g.N = D; g.K = DFF; g.w_bf16 = h->w2_bf + (size_t)l * D * DFF;
+        g.a_bf16 = (const bf16*)h->ws_hid; g.bias = w + lo.b2; g.residual = h->ws_h;
+        g.out_f32 = 1; g.out[0] = h->ws_h;
+        if ((rc = gemm_tc(h, g, s))) return rc;
+      }
+      continue;
+    }
     {  // a = LN1(h); q,k,v = a W^T + b        (transformer.py:235-236, :281-284)
       GemmArgs g = {};
       g.A = h->ws_h; g.W = h->wqkv + (size_t)l * 3 * D * D; g.bias = h->bqkv + (size_t)l * 3 * D;
       g.M = M; g.N = 3 * D; g.K = D;
       g.ln_g = w + lo.ln1_g; g.ln_b = w + lo.ln1_b;
       g.out[0] = h->ws_q; g.out[1] = h->ws_k; g.out[2] = h->ws_v; g.out_split = D;
-      g.out_is_bf16 = bf;
       if ((rc = gemm(h, g, s))) return rc;
     }
-    if ((rc = attention(h, h->ws_q, h->ws_k, h->ws_v, h->ws_o, bf ? VADB_BF16 : VADB_F32, lengths,
-                        Bc, T, s)))
+    if ((rc = attention(h, h->ws_q, h->ws_k, h->ws_v, h->ws_o, VADB_F32, lengths, Bc, T, s)))
       return rc;
     {  // h += o Wo^T + bo                      (transformer.py:347, :237)
       GemmArgs g = {};
-      g.A = h->ws_o; g.a_is_bf16 = bf; g.W = w + lo.wo; g.bias = w + lo.bo;
+      g.A = h->ws_o; g.W = w + lo.wo; g.bias = w + lo.bo;
       g.M = M; g.N = D; g.K = D; g.residual = h->ws_h;
       g.out[0] = h->ws_h; g.out_split = D;
       if ((rc = gemm(h, g, s))) return rc;
@@ -291,6 +332,7 @@ int vadb_create(vadb_handle** out, const vadb_config* cfg, int device) {
   h->cfg = *cfg;
   h->device = device;
   h->lay = make_layout(cfg->feature_size, cfg->num_layers);
+  h->num_sms = prop.multiProcessorCount;
   DeviceGuard dg(device);
   e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete h; return fail(nullptr, VADB_E_CUDA, m); }

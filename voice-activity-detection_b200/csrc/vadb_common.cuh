@@ -65,6 +65,22 @@ cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o,
                            const int32_t* lengths, int B, int T, cudaStream_t s,
                            std::string* err);
 
+// tcgen05 GEMM for the per-frame Linears in bf16 mode (k_gemm_tc.cu)
+struct GemmTcArgs {
+  int M, N, K;
+  const bf16* w_bf16;      // [N, K]
+  const bf16* a_bf16;      // [M, K] (when ln_g == nullptr)
+  const float* a_f32;      // [M, 128] fp32 rows through LayerNorm (when ln_g != nullptr)
+  const float* ln_g;
+  const float* ln_b;
+  const float* bias;       // [N] fp32
+  int relu;
+  const float* residual;   // fp32 [M,128] or nullptr (may alias out[0])
+  int out_f32;             // fp32 [M,N] output, else bf16
+  void* out[3];            // out[1], out[2] set -> columns split in 128-wide blocks (q, k, v)
+};
+cudaError_t launch_gemm_tc(const GemmTcArgs& a, int num_sms, cudaStream_t s, std::string* err);
+
 // final LayerNorm + classifier + sigmoid/log-softmax (k_classifier.cu)
 cudaError_t launch_classifier(const float* h, const float* g, const float* b, const float* wc,
                               const float* bc, int M, float* prob, float* logp, cudaStream_t s);
