@@ -6,19 +6,25 @@
 // padding mask), :333 (softmax over keys), :338-346 (P V and the head merge) -- the three
 // [B,1,T,T] fp32 score tensors the reference materialises never leave the SM.
 //
-// Work decomposition (one CTA = one clip x 256 query rows = two 128-row query tiles):
-//   warp 8      TMA producer: Q (once) and a 3-stage ring of 64-key K/V tiles, 128B-swizzled
-//   warp 9      MMA issuer (one elected thread): S_t = Q_t K^T and O_t += P_t V via tcgen05.mma,
-//               accumulators in TMEM (S: 2 x 64 columns, O: 2 x 128 columns)
+// Persistent CTAs (one per SM) walk a static list of work items; one item = one clip x 256 query rows
+// = two 128-row query tiles:
+//   warp 8      TMA producer: Q (once), a 4-stage ring of 64-key K tiles and a 3-stage ring of V
+//               tiles, all 128B-swizzled
+//   warp 9      MMA issuer (one elected lane): S_t = Q_t K^T and O_t += P_t V via tcgen05.mma with
+//               accumulators in TMEM -- S double-buffered per query tile (4 x 64 columns),
+//               O 2 x 128 columns.  Q K^T of step j+2 is issued right behind P V of step j, so the
+//               scores of the next step are already in TMEM when a softmax warpgroup finishes a step.
 //   warps 0-3   softmax warpgroup of query tile 0: one thread per query row (TMEM lane),
 //   warps 4-7   softmax warpgroup of query tile 1   tcgen05.ld S -> online softmax (fp32, exp2,
 //               lazy rescale of O in TMEM) -> P (bf16) into swizzled shared memory
-// The two query tiles share every K/V tile and ping-pong on the tensor pipe: while the softmax
-// of one tile runs on the CUDA cores, the MMAs of the other tile run on the tensor cores.
+// The two query tiles share every K/V tile and ping-pong on the tensor pipe.
 //
 // Algorithmic traffic per launch: read Q,K,V once + write O once = 4*B*T*128*2 bytes (SURVEY.md
 // section 8d); K/V re-reads by the other query pairs of a clip are served from L2.
 #include <math_constants.h>
+#include <stdlib.h>
+
+#include <vector>
 
 #include "tc_common.cuh"
 #include "vadb_common.cuh"
@@ -30,40 +36,72 @@ using namespace tc;
 
 constexpr int BM = 128;          // query rows per tile (UMMA M)
 constexpr int BKV = 64;          // keys per K/V tile
-constexpr int NSTAGE = 3;
+constexpr int NK = 4;            // K ring depth (K runs two steps ahead of V)
+constexpr int NV = 2;            // V ring depth
 constexpr int NTHREADS = 320;    // 8 softmax warps + producer + MMA
 
 constexpr uint32_t Q_HALF_BYTES = BM * 128;          // [128 rows x 64 d] bf16 = 16 KB
 constexpr uint32_t Q_TILE_BYTES = 2 * Q_HALF_BYTES;  // two d-halves
 constexpr uint32_t KV_HALF_BYTES = BKV * 128;        // [64 keys x 64 d] = 8 KB
-constexpr uint32_t K_TILE_BYTES = 2 * KV_HALF_BYTES;
-constexpr uint32_t STAGE_BYTES = 2 * K_TILE_BYTES;   // K + V
+constexpr uint32_t KV_TILE_BYTES = 2 * KV_HALF_BYTES;
 constexpr uint32_t P_TILE_BYTES = BM * 128;          // [128 rows x 64 keys] bf16 = 16 KB
 
 constexpr uint32_t OFF_Q = 0;
-constexpr uint32_t OFF_KV = OFF_Q + 2 * Q_TILE_BYTES;
-constexpr uint32_t OFF_P = OFF_KV + NSTAGE * STAGE_BYTES;
-constexpr uint32_t OFF_BAR = OFF_P + 2 * P_TILE_BYTES;
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 256;
+constexpr uint32_t OFF_K = OFF_Q + 2 * Q_TILE_BYTES;
+constexpr uint32_t OFF_V = OFF_K + NK * KV_TILE_BYTES;
+constexpr uint32_t OFF_OST = OFF_V + NV * KV_TILE_BYTES;        // O staging: [tile][d half] x 16 KB
+constexpr uint32_t OFF_BAR = OFF_OST + 4 * P_TILE_BYTES;
+constexpr uint32_t OFF_SCR = OFF_BAR + 256;        // 256 floats of scratch + one zero word (token pinning)
+constexpr uint32_t SMEM_BYTES = OFF_SCR + 1024 + 64;
 constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;   // slack for 1024-byte alignment
 
 // barrier slots (8 bytes each) at OFF_BAR
-enum { B_QFULL = 0, B_KFULL = 1, B_VFULL = 4, B_EMPTY = 7, B_SFULL = 10, B_PFULL = 12, B_OFULL = 14,
-       B_COUNT = 16 };
+enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 5, B_VFULL = 9, B_VEMPTY = 12, B_SFULL = 15 /* [t][buf] */,
+       B_PFULL = 19, B_OFULL = 21, B_QEMPTY = 23, B_COUNT = 24 };
+static_assert(NK <= 4 && NV <= 3, "barrier slots");
 
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TM_S = 0;      // S_t at columns [64 t, 64 t + 64)
-constexpr uint32_t TM_O = 128;    // O_t at columns [128 + 128 t, +128)
+constexpr uint32_t TM_S = 0;      // S_t[buf] at columns (2 t + buf) * 64; P_t (bf16 pairs, 32 columns)
+                                  // overwrites the head of the S buffer it was computed from
+constexpr uint32_t TM_O = 256;    // O_t at columns 256 + 128 t
 
 constexpr uint32_t IDESC_QK = idesc_bf16(128, BKV, 0, 0);   // A = Q (K-major), B = K (K-major)
 constexpr uint32_t IDESC_PV = idesc_bf16(128, 128, 0, 1);   // A = P (K-major), B = V (MN-major)
 
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units: rescale O only when the max grew > 2^8
 
+// TRACE: developer instrumentation -- CTA 0 records clock64() stamps of the pipeline events of its
+// second work item into `trace` (VADB_ATTN_TRACE=1); compiled out of the production instantiation.
+#define TR(slot) do { if (TRACE && blockIdx.x == 0 && n_item == 1 && trace) trace[(slot)] = clock64(); } while (0)
+
+struct Item { int b, q0, len, nkv, ntile; };
+
+__device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// named barriers: 1/2 = MUFU token (softmax warpgroup 0 / 1 may run its exponentials), 3+t = warpgroup t
+enum { NB_TOKEN0 = 1, NB_TOKEN1 = 2, NB_WG = 3 };
+
+__device__ __forceinline__ Item get_item(int idx, int npairs, int T, const int32_t* lengths) {
+  Item it;
+  it.b = idx / npairs;
+  it.q0 = (idx % npairs) * 2 * BM;
+  int len = lengths ? lengths[it.b] : T;
+  it.len = min(max(len, 0), T);
+  it.nkv = (it.len + BKV - 1) / BKV;
+  it.ntile = (it.q0 + BM < T) ? 2 : 1;        // second query tile entirely past T: skip it
+  return it;
+}
+
+template <bool TRACE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-               const __grid_constant__ CUtensorMap tm_v, bf16* __restrict__ O,
-               const int32_t* __restrict__ lengths, int T, int npairs) {
+               const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
+               bf16* __restrict__ O, const int32_t* __restrict__ lengths, int T, int npairs, int n_items,
+               long long* trace) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -72,40 +110,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_BAR + 8 * B_COUNT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x / npairs, pair = blockIdx.x % npairs;
-  const int q0 = pair * 2 * BM;
-  int len = lengths ? lengths[b] : T;
-  len = min(max(len, 0), T);
-  const int nkv = (len + BKV - 1) / BKV;
-  const int ntile = (q0 + BM < T) ? 2 : 1;       // second query tile entirely past T: skip it
-
-  if (nkv == 0) {
-    // every key masked: softmax of all -inf -> NaN rows, as the reference produces
-    for (int i = threadIdx.x; i < 2 * BM * (D / 2); i += NTHREADS) {
-      const int r = q0 + i / (D / 2), c = (i % (D / 2)) * 2;
-      if (r < T) *reinterpret_cast<uint32_t*>(O + ((long)b * T + r) * D + c) = 0x7FC07FC0u;
-    }
-    return;
-  }
 
   if (threadIdx.x == 0) {
     mbar_init(BAR(B_QFULL), 1);
-    for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(BAR(B_KFULL + s), 1);
-      mbar_init(BAR(B_VFULL + s), 1);
-      mbar_init(BAR(B_EMPTY + s), 1);
-    }
+    mbar_init(BAR(B_QEMPTY), 1);
+    for (int s = 0; s < NK; ++s) { mbar_init(BAR(B_KFULL + s), 1); mbar_init(BAR(B_KEMPTY + s), 1); }
+    for (int s = 0; s < NV; ++s) { mbar_init(BAR(B_VFULL + s), 1); mbar_init(BAR(B_VEMPTY + s), 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(BAR(B_SFULL + i), 1);
     for (int t = 0; t < 2; ++t) {
-      mbar_init(BAR(B_SFULL + t), 1);
-      mbar_init(BAR(B_PFULL + t), 128);
+      mbar_init(BAR(B_PFULL + t), 4);          // one arrival per softmax warp
       mbar_init(BAR(B_OFULL + t), 1);
     }
     mbar_fence_init();
+    *reinterpret_cast<volatile float*>(smem_gen + OFF_SCR + 1024) = 0.f;
   }
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_o);
   }
   if (warp == 9) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
   tc_fence_before();
@@ -116,118 +139,242 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   if (warp == 8) {
     // ======================= TMA producer =======================
     if (lane == 0) {
-      mbar_arrive_expect_tx(BAR(B_QFULL), ntile * Q_TILE_BYTES);
-      for (int t = 0; t < ntile; ++t)
-        for (int hf = 0; hf < 2; ++hf)
-          tma_load_3d(smem_base + OFF_Q + t * Q_TILE_BYTES + hf * Q_HALF_BYTES, &tm_q, BAR(B_QFULL),
-                      hf * 64, q0 + t * BM, b);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j % NSTAGE;
-        mbar_wait(BAR(B_EMPTY + s), ((j / NSTAGE) & 1) ^ 1, 1);
-        const uint32_t kdst = smem_base + OFF_KV + s * STAGE_BYTES;
-        mbar_arrive_expect_tx(BAR(B_KFULL + s), K_TILE_BYTES);
-        tma_load_3d(kdst, &tm_k, BAR(B_KFULL + s), 0, j * BKV, b);
-        tma_load_3d(kdst + KV_HALF_BYTES, &tm_k, BAR(B_KFULL + s), 64, j * BKV, b);
-        mbar_arrive_expect_tx(BAR(B_VFULL + s), K_TILE_BYTES);
-        tma_load_3d(kdst + K_TILE_BYTES, &tm_v, BAR(B_VFULL + s), 0, j * BKV, b);
-        tma_load_3d(kdst + K_TILE_BYTES + KV_HALF_BYTES, &tm_v, BAR(B_VFULL + s), 64, j * BKV, b);
+      int kc = 0, vc = 0, nq = 0;              // K tiles / V tiles / Q loads issued so far
+      for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
+        const Item it = get_item(idx, npairs, T, lengths);
+        if (it.nkv == 0) continue;
+        mbar_wait(BAR(B_QEMPTY), (nq & 1) ^ 1, 1);            // every Q K^T of the previous item retired
+        mbar_arrive_expect_tx(BAR(B_QFULL), it.ntile * Q_TILE_BYTES);
+        for (int t = 0; t < it.ntile; ++t)
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_3d(smem_base + OFF_Q + t * Q_TILE_BYTES + hf * Q_HALF_BYTES, &tm_q, BAR(B_QFULL),
+                        hf * 64, it.q0 + t * BM, it.b);
+        ++nq;
+        auto load_k = [&](int j) {
+          const int ks = (kc + j) % NK;
+          mbar_wait(BAR(B_KEMPTY + ks), (((kc + j) / NK) & 1) ^ 1, 2);
+          const uint32_t kdst = smem_base + OFF_K + ks * KV_TILE_BYTES;
+          mbar_arrive_expect_tx(BAR(B_KFULL + ks), KV_TILE_BYTES);
+          tma_load_3d(kdst, &tm_k, BAR(B_KFULL + ks), 0, j * BKV, it.b);
+          tma_load_3d(kdst + KV_HALF_BYTES, &tm_k, BAR(B_KFULL + ks), 64, j * BKV, it.b);
+        };
+        // K runs two steps ahead of V, in the order the MMA warp consumes them
+        load_k(0);
+        if (it.nkv > 1) load_k(1);
+        for (int j = 0; j < it.nkv; ++j) {
+          if (j + 2 < it.nkv) load_k(j + 2);
+          const int vs = (vc + j) % NV;
+          mbar_wait(BAR(B_VEMPTY + vs), (((vc + j) / NV) & 1) ^ 1, 3);
+          const uint32_t vdst = smem_base + OFF_V + vs * KV_TILE_BYTES;
+          mbar_arrive_expect_tx(BAR(B_VFULL + vs), KV_TILE_BYTES);
+          tma_load_3d(vdst, &tm_v, BAR(B_VFULL + vs), 0, j * BKV, it.b);
+          tma_load_3d(vdst + KV_HALF_BYTES, &tm_v, BAR(B_VFULL + vs), 64, j * BKV, it.b);
+        }
+        kc += it.nkv; vc += it.nkv;
       }
     }
   } else if (warp == 9) {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
-      auto issue_qk = [&](int t, int s) {
-        // S_t[128 x 64] = Q_t[128 x 128] K[64 x 128]^T : 8 MMAs of K = 16 (two 64-wide d halves)
-        const uint32_t qa = smem_base + OFF_Q + t * Q_TILE_BYTES;
-        const uint32_t kb = smem_base + OFF_KV + s * STAGE_BYTES;
+    // The whole warp walks the schedule (waits included) and one elected lane issues, so the
+    // descriptor arithmetic stays warp-uniform and costs an add or two per MMA.
+    const uint32_t q_lo = desc_lo(smem_base + OFF_Q, 16);
+    const uint32_t k_lo = desc_lo(smem_base + OFF_K, 16);
+    const uint32_t v_lo = desc_lo(smem_base + OFF_V, KV_HALF_BYTES);   // LBO = stride between d halves
+    auto issue_qk = [&](int t, int ks, int buf) {
+      // S_t[buf][128 x 64] = Q_t[128 x 128] K[64 x 128]^T : 8 MMAs of K = 16 (two 64-wide d halves)
+      const uint32_t qa = q_lo + (uint32_t)t * (Q_TILE_BYTES >> 4);
+      const uint32_t kb = k_lo + (uint32_t)ks * (KV_TILE_BYTES >> 4);
+      const uint32_t d = tmem_base + TM_S + (uint32_t)(2 * t + buf) * 64;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_ss(tmem_base + TM_S + 64 * t, desc_kmajor_sw128(qa + hf * Q_HALF_BYTES + kk * 32),
-                    desc_kmajor_sw128(kb + hf * KV_HALF_BYTES + kk * 32), IDESC_QK, (hf | kk) != 0);
-      };
-      auto issue_pv = [&](int t, int s, bool accumulate) {
-        // O_t[128 x 128] += P_t[128 x 64] V[64 x 128] : 4 MMAs of K = 16 keys, N = 128 (two d halves)
-        const uint32_t pa = smem_base + OFF_P + t * P_TILE_BYTES;
-        const uint32_t vb = smem_base + OFF_KV + s * STAGE_BYTES + K_TILE_BYTES;
+      for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_ss(tmem_base + TM_O + 128 * t, desc_kmajor_sw128(pa + kk * 32),
-                  desc_mnmajor_sw128(vb + kk * 2048, KV_HALF_BYTES, 1024), IDESC_PV,
-                  (accumulate || kk != 0) ? 1u : 0u);
-      };
-      mbar_wait(BAR(B_QFULL), 0, 2);
-      mbar_wait(BAR(B_KFULL + 0), 0, 3);
-      tc_fence_after();
-      for (int t = 0; t < ntile; ++t) {
-        issue_qk(t, 0);
-        umma_commit(BAR(B_SFULL + t));
-      }
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j % NSTAGE, sn = (j + 1) % NSTAGE;
-        for (int t = 0; t < ntile; ++t) {
-          mbar_wait(BAR(B_PFULL + t), j & 1, 4);              // P_t(j) in smem, S_t consumed, O_t corrected
-          if (t == 0) mbar_wait(BAR(B_VFULL + s), (j / NSTAGE) & 1, 5);
-          tc_fence_after();
-          issue_pv(t, s, j > 0);
-          umma_commit(BAR(B_OFULL + t));
-          if (t == ntile - 1) umma_commit(BAR(B_EMPTY + s)); // K/V stage s free once these MMAs retire
-          if (j + 1 < nkv) {
-            if (t == 0) { mbar_wait(BAR(B_KFULL + sn), ((j + 1) / NSTAGE) & 1, 6); tc_fence_after(); }
-            issue_qk(t, sn);
-            umma_commit(BAR(B_SFULL + t));
+          umma_ss_lh(d, qa + hf * (Q_HALF_BYTES >> 4) + kk * 2, kb + hf * (KV_HALF_BYTES >> 4) + kk * 2,
+                     DESC_HI_SW128, IDESC_QK, (hf | kk) != 0 ? 1u : 0u);
+    };
+    auto issue_pv = [&](int t, int vs, int buf, uint32_t accumulate) {
+      // O_t[128 x 128] += P_t[128 x 64] V[64 x 128] : 4 MMAs of K = 16 keys, N = 128 (two d halves);
+      // P_t is read from TMEM (the head of S_t[buf]), V from shared memory
+      const uint32_t pa = tmem_base + TM_S + (uint32_t)(2 * t + buf) * 64;
+      const uint32_t vb = v_lo + (uint32_t)vs * (KV_TILE_BYTES >> 4);
+      const uint32_t d = tmem_base + TM_O + 128u * t;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        umma_ts_lh(d, pa + kk * 8, vb + kk * (2048 >> 4), DESC_HI_SW128, IDESC_PV,
+                   kk != 0 ? 1u : accumulate);
+    };
+    int kc = 0, vc = 0, nq = 0, n_item = 0;
+    int g[2] = {0, 0};                          // softmax steps issued so far, per query tile
+    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n_item) {
+      const Item it = get_item(idx, npairs, T, lengths);
+      if (it.nkv == 0) continue;
+      const int nkv = it.nkv, ntile = it.ntile;
+      TR(0);
+      mbar_wait(BAR(B_QFULL), nq & 1, 4);
+      ++nq;
+      // prologue: scores of steps 0 and 1 for both query tiles
+      for (int j = 0; j < 2 && j < nkv; ++j) {
+        const int ks = (kc + j) % NK;
+        mbar_wait(BAR(B_KFULL + ks), ((kc + j) / NK) & 1, 5);
+        tc_fence_after();
+        if (elect_one()) {
+          for (int t = 0; t < ntile; ++t) {
+            issue_qk(t, ks, (g[t] + j) & 1);
+            umma_commit(BAR(B_SFULL + 2 * t + ((g[t] + j) & 1)));
           }
+          umma_commit(BAR(B_KEMPTY + ks));
+          if (j == nkv - 1) umma_commit(BAR(B_QEMPTY));
+        }
+        __syncwarp();
+      }
+      TR(1);
+      for (int j = 0; j < nkv; ++j) {
+        const int vs = (vc + j) % NV, kn = (kc + j + 2) % NK;
+        const bool more = j + 2 < nkv;
+        mbar_wait(BAR(B_VFULL + vs), ((vc + j) / NV) & 1, 6);
+        if (more) mbar_wait(BAR(B_KFULL + kn), ((kc + j + 2) / NK) & 1, 7);
+        for (int t = 0; t < ntile; ++t) {
+          TR(64 + j * 16 + t * 4 + 0);
+          mbar_wait(BAR(B_PFULL + t), (g[t] + j) & 1, 8);   // P_t(j) in smem, S_t consumed, O_t corrected
+          tc_fence_after();
+          TR(64 + j * 16 + t * 4 + 1);
+          if (elect_one()) {
+            issue_pv(t, vs, (g[t] + j) & 1, j > 0 ? 1u : 0u);
+            umma_commit(BAR(B_OFULL + t));
+            if (t == ntile - 1) umma_commit(BAR(B_VEMPTY + vs));
+            if (more) {
+              issue_qk(t, kn, (g[t] + j) & 1);
+              umma_commit(BAR(B_SFULL + 2 * t + ((g[t] + j) & 1)));
+              if (t == ntile - 1) {
+                umma_commit(BAR(B_KEMPTY + kn));
+                if (j + 2 == nkv - 1) umma_commit(BAR(B_QEMPTY));   // last Q K^T of this item issued
+              }
+            }
+          }
+          __syncwarp();
+          TR(64 + j * 16 + t * 4 + 3);
         }
       }
+      kc += nkv; vc += nkv;
+      for (int t = 0; t < ntile; ++t) g[t] += nkv;
     }
-  } else if (warp < 4 * ntile) {
+  } else {
     // ======================= softmax warpgroups =======================
     const int t = warp >> 2;                       // query tile of this warpgroup
     const int row = (warp & 3) * 32 + lane;        // row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t ts = tmem_base + lane_addr + TM_S + 64 * t;
+    const uint32_t ts = tmem_base + lane_addr + TM_S + 128 * t;
     const uint32_t to = tmem_base + lane_addr + TM_O + 128 * t;
-    unsigned char* p_row = smem_gen + OFF_P + t * P_TILE_BYTES;
+    unsigned char* ost = smem_gen + OFF_OST + t * 2 * P_TILE_BYTES;
+    volatile float* scratch = reinterpret_cast<volatile float*>(smem_gen + OFF_SCR);
     // softmax in the exp2 domain: p = 2^(s*c - m), c = log2(e)/sqrt(d_head)  (transformer.py:362)
     const float c = 1.4426950408889634f * 0.08838834764831845f;
-    float m_ref = -CUDART_INF_F;     // reference max (log2 domain) the stored P/O are relative to
-    float l_sum = 0.f;
+    int g = 0, n_item = 0;                         // softmax steps done so far by this warpgroup
+    // The two warpgroups take turns on the SFU: exp2 throughput (16/clk/SM) is the scarce resource of
+    // this kernel, so their exponential phases are serialised with a token and everything else
+    // (TMEM traffic, row max, barrier traffic) of one overlaps the exponentials of the other.
+    if (t == 1) nbar_arrive(NB_TOKEN0, 256);       // warpgroup 0 goes first
 
-    for (int j = 0; j < nkv; ++j) {
-      mbar_wait(BAR(B_SFULL + t), j & 1, 7);
-      tc_fence_after();
-      uint32_t sv[2][32];
-      tmem_ld32(ts, sv[0]);
-      tmem_ld32(ts + 32, sv[1]);
-      tmem_ld_wait();
-      const int kbase = j * BKV;
-      if (kbase + BKV > len) {                     // warp-uniform: only the last tile holds masked keys
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2)
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kbase + h2 * 32 + i >= len) sv[h2][i] = 0xFF800000u;   // -inf
+#define TS(k) do { if (TRACE && (threadIdx.x & 127) == 0) TR(512 + j * 32 + t * 16 + (k)); } while (0)
+    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n_item) {
+      const Item it = get_item(idx, npairs, T, lengths);
+      const int nkv = it.nkv, len = it.len;
+      if (nkv == 0) {
+        // every key masked: softmax of all -inf -> NaN rows, as the reference produces
+        const int qrow = it.q0 + t * BM + row;
+        bf16* orow = O + ((long)it.b * T + qrow) * D;
+        if (qrow < T)
+          for (int cgi = 0; cgi < D / 8; ++cgi)
+            *reinterpret_cast<uint4*>(orow + cgi * 8) = make_uint4(0x7FC07FC0u, 0x7FC07FC0u, 0x7FC07FC0u, 0x7FC07FC0u);
+        continue;
       }
-      // row max with 4 independent chains (ILP: one thread owns the whole row)
-      float mx4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+      if (t >= it.ntile) continue;
+      const bool pingpong = it.ntile == 2;
+      float m_ref = -CUDART_INF_F;     // reference max (log2 domain) the stored P/O are relative to
+      float l_sum = 0.f;
+
+      bool s_ready = false;          // result of the poll issued one step ahead (hides the probe latency)
+      for (int j = 0; j < nkv; ++j, ++g) {
+        TS(0);
+        if (!s_ready) mbar_wait(BAR(B_SFULL + 2 * t + (g & 1)), (g >> 1) & 1, 9);
+        tc_fence_after();
+        TS(1);
+        const uint32_t tsb = ts + (g & 1) * 64;
+        uint32_t sv[2][32];
+        tmem_ld32(tsb, sv[0]);
+        tmem_ld32(tsb + 32, sv[1]);
+        // non-blocking probes, consumed later: "P V of the previous step retired", "next S ready"
+        const bool o_ready = (j == 0) || mbar_test_wait(BAR(B_OFULL + t), (g - 1) & 1);
+        s_ready = (j + 1 < nkv) && mbar_test_wait(BAR(B_SFULL + 2 * t + ((g + 1) & 1)), ((g + 1) >> 1) & 1);
+        tmem_ld_wait();
+        TS(2);
+        const int kbase = j * BKV;
+        if (kbase + BKV > len) {                     // warp-uniform: only the last tile holds masked keys
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(sv[0][i]), __uint_as_float(sv[0][i + 1])));
-        mx4[((i >> 1) + 2) & 3] = fmaxf(mx4[((i >> 1) + 2) & 3], fmaxf(__uint_as_float(sv[1][i]), __uint_as_float(sv[1][i + 1])));
-      }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      const float mxl = mx * c;
-      if (j == 0) {
-        m_ref = mxl;
-      } else {
-        const bool grow = mxl > m_ref + RESCALE_THRESHOLD;
-        // previous P V must have retired before O is touched or the P buffer is rewritten
-        mbar_wait(BAR(B_OFULL + t), (j - 1) & 1, 8);
-        if (__any_sync(0xffffffffu, grow)) {       // warp-uniform: tcgen05.ld/st are .sync.aligned
-          tc_fence_after();
+          for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (kbase + h2 * 32 + i >= len) sv[h2][i] = 0xFF800000u;   // -inf
+        }
+        auto row_max = [&]() {                       // 4 independent chains (one thread owns the row)
+          float mx4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(sv[0][i]), __uint_as_float(sv[0][i + 1])));
+            mx4[((i >> 1) + 2) & 3] = fmaxf(mx4[((i >> 1) + 2) & 3], fmaxf(__uint_as_float(sv[1][i]), __uint_as_float(sv[1][i + 1])));
+          }
+          return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * c;
+        };
+        uint32_t pk[32];
+        float psum, p_last;
+        auto exps = [&](float m_use, bool pinned) {
+          float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            const float a0 = fmaf(__uint_as_float(sv[i >> 5][i & 31]), c, -m_use);
+            const float a1 = fmaf(__uint_as_float(sv[(i + 1) >> 5][(i + 1) & 31]), c, -m_use);
+            const float p0 = pinned ? fast_exp2_pinned(a0) : fast_exp2(a0);
+            const float p1 = pinned ? fast_exp2_pinned(a1) : fast_exp2(a1);
+            ps4[(i >> 1) & 3] += p0 + p1;
+            pk[i >> 1] = pack_bf16(p0, p1);
+            if (i == 62) p_last = p1;
+          }
+          psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+        };
+        // The exponentials of step j > 0 start from the PREVIOUS reference max (no wait for this
+        // tile's row max, which is computed alongside on otherwise idle issue slots); only if the max
+        // grew by more than 2^8 is the step redone against the new reference (rare).
+        if (j == 0) m_ref = row_max();
+        TS(3);
+        float m_use = m_ref;
+        if (pingpong) {
+          nbar_sync(t == 0 ? NB_TOKEN0 : NB_TOKEN1, 256);
+          // data dependence on a load issued after the barrier: keeps ptxas from hoisting the
+          // exponentials above the token wait
+          m_use += scratch[256];
+        }
+        exps(m_use, true);
+        const float mxl = (j == 0) ? m_ref : row_max();
+        if (pingpong) {
+          // ... and the token is handed over once the last exponential has been through the SFU (the
+          // sums / packing / row max that follow need no SFU and may trail behind the hand-over)
+          scratch[threadIdx.x] = p_last;
+          nbar_arrive(t == 0 ? NB_TOKEN1 : NB_TOKEN0, 256);
+        }
+        TS(4);
+        float alpha = 1.f;
+        const bool rescale = (j > 0) && __any_sync(0xffffffffu, mxl > m_ref + RESCALE_THRESHOLD);
+        if (rescale) {                               // warp-uniform, rare
           const float m_new = fmaxf(m_ref, mxl);
-          const float alpha = (m_new == -CUDART_INF_F) ? 1.f : fast_exp2(m_ref - m_new);
+          alpha = fast_exp2(m_ref - m_new);
+          m_ref = m_new;
+          exps(m_ref, false);
+        }
+        l_sum = l_sum * alpha + psum;
+        // previous P V must have retired before O is rescaled (P itself lives in this step's S buffer)
+        if (rescale) {
+          if (!o_ready) mbar_wait(BAR(B_OFULL + t), (g - 1) & 1, 10);
+          tc_fence_after();
 #pragma unroll 1
           for (int cb = 0; cb < 4; ++cb) {
             uint32_t ov[32];
@@ -237,59 +384,64 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
             tmem_st32(to + cb * 32, ov);
           }
-          tmem_st_wait();
-          l_sum *= alpha;
-          m_ref = m_new;
         }
+        TS(5);
+        tmem_st32(tsb, pk);                          // P_t (bf16 pairs) over the head of S_t[buf]
+        // An mbarrier may run at most one phase ahead of its waiter: do not signal P_t(j) before the
+        // MMA warp has consumed P_t(j-1) (it has once P V(j-1) retired).  The probe was issued at the
+        // top of the step, so this is normally free.
+        if (!o_ready && !rescale) mbar_wait(BAR(B_OFULL + t), (g - 1) & 1, 12);
+        tmem_st_wait();
+        TS(6);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_PFULL + t));
+        TS(7);
       }
-      const float m_use = (m_ref == -CUDART_INF_F) ? 0.f : m_ref;
-      float ps4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {             // 8 chunks of 8 keys = 16 bytes of bf16 each
-        uint32_t pk[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i0 = ch * 8 + e * 2;
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[i0 >> 5][i0 & 31]), c, -m_use));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[(i0 + 1) >> 5][(i0 + 1) & 31]), c, -m_use));
-          ps4[e] += p0 + p1;
-          pk[e] = pack_bf16(p0, p1);
-        }
-        *reinterpret_cast<uint4*>(p_row + sw128_offset(row, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
-      const float psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
-      l_sum += psum;
-      fence_proxy_async_smem();     // generic-proxy P writes -> visible to the tensor core (async proxy)
-      tc_fence_before();
-      mbar_arrive(BAR(B_PFULL + t));
-    }
 
-    // epilogue: O_t / l -> bf16 -> global
-    mbar_wait(BAR(B_OFULL + t), (nkv - 1) & 1, 9);
-    tc_fence_after();
-    const float inv = 1.0f / l_sum;
-    const int qrow = q0 + t * BM + row;
-    bf16* orow = O + ((long)b * T + qrow) * D;
+      // epilogue: O_t / l -> bf16 -> two 128B-swizzled staging tiles (64 columns each) -> TMA stores in
+      // full lines; rows past T are clipped by the tensor map.  The next item's first P V (which
+      // overwrites O_t) is ordered behind these TMEM reads by this warp's own next p_full arrival.
+      if (TRACE && (threadIdx.x & 127) == 0) TR(32 + t * 4 + 0);
+      mbar_wait(BAR(B_OFULL + t), (g - 1) & 1, 11);
+      tc_fence_after();
+      if (TRACE && (threadIdx.x & 127) == 0) TR(32 + t * 4 + 1);
+      const float inv = 1.0f / l_sum;
+      // the staging tiles were handed to the TMA engine one whole item ago: formal guarantee only
+      if ((threadIdx.x & 127) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      nbar_sync(NB_WG + t, 128);
 #pragma unroll 1
-    for (int cb = 0; cb < 4; ++cb) {
-      uint32_t ov[32];
-      tmem_ld32(to + cb * 32, ov);
-      tmem_ld_wait();
-      if (qrow < T) {
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t ov[2][32];
+        tmem_ld32(to + hf * 64, ov[0]);
+        tmem_ld32(to + hf * 64 + 32, ov[1]);
+        tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 pk;
-          pk.x = pack_bf16(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv);
-          pk.y = pack_bf16(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv);
-          pk.z = pack_bf16(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv);
-          pk.w = pack_bf16(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + cb * 32 + g * 8) = pk;
+        for (int ch = 0; ch < 8; ++ch) {
+          uint4 o4;
+          const uint32_t* src = &ov[ch >> 2][(ch & 3) * 8];
+          o4.x = pack_bf16(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+          o4.y = pack_bf16(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+          o4.z = pack_bf16(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+          o4.w = pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+          *reinterpret_cast<uint4*>(ost + hf * P_TILE_BYTES + sw128_offset(row, ch)) = o4;
         }
       }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      nbar_sync(NB_WG + t, 128);
+      if ((threadIdx.x & 127) == 0) {
+        const uint32_t src = smem_base + OFF_OST + t * 2 * P_TILE_BYTES;
+        tma_store_3d(&tm_o, src, 0, it.q0 + t * BM, it.b);
+        tma_store_3d(&tm_o, src + P_TILE_BYTES, 64, it.q0 + t * BM, it.b);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (TRACE && (threadIdx.x & 127) == 0) TR(32 + t * 4 + 2);
     }
-    tc_fence_before();
   }
 
+  if (warp < 8 && (threadIdx.x & 127) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
   if (warp == 9) {
     tc_fence_after();
@@ -312,22 +464,65 @@ CUresult make_tmap_bt128(CUtensorMap* map, const void* base, int B, int T, int b
 
 cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o, const int32_t* lengths,
                            int B, int T, cudaStream_t s, std::string* err) {
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
   if (B <= 0 || T <= 0) return cudaSuccess;
-  CUtensorMap tq, tk, tv;
+  CUtensorMap tq, tk, tv, to;
   CUresult r;
-  if ((r = make_tmap_bt128(&tq, q, B, T, BM)) != CUDA_SUCCESS ||
+  if ((r = make_tmap_bt128(&to, o, B, T, BM)) != CUDA_SUCCESS ||
+      (r = make_tmap_bt128(&tq, q, B, T, BM)) != CUDA_SUCCESS ||
       (r = make_tmap_bt128(&tk, k, B, T, BKV)) != CUDA_SUCCESS ||
       (r = make_tmap_bt128(&tv, v, B, T, BKV)) != CUDA_SUCCESS) {
     if (err) *err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")";
     return cudaErrorInvalidValue;
   }
-  cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const int npairs = (T + 2 * BM - 1) / (2 * BM);
+  const long n_items_l = (long)B * npairs;
+  if (n_items_l > 0x7fffffffL) return cudaErrorInvalidValue;
+  const int n_items = (int)n_items_l;
+  const long grid = n_items < num_sms ? n_items : num_sms;
+  static const bool want_trace = getenv("VADB_ATTN_TRACE") != nullptr;
+  if (want_trace) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)SMEM_ALLOC);
+    if (e != cudaSuccess) return e;
+    long long* dtrace = nullptr;
+    const int NTR = 2048;
+    cudaMalloc(&dtrace, NTR * sizeof(long long));
+    cudaMemsetAsync(dtrace, 0, NTR * sizeof(long long), s);
+    attn_tc_kernel<true><<<(unsigned)grid, NTHREADS, SMEM_ALLOC, s>>>(tq, tk, tv, to, o, lengths, T, npairs, n_items, dtrace);
+    std::vector<long long> ht(NTR);
+    cudaMemcpyAsync(ht.data(), dtrace, NTR * sizeof(long long), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    cudaFree(dtrace);
+    const long long t0 = ht[0];
+    auto rel = [&](int i) { return ht[i] ? (long long)(ht[i] - t0) : -1LL; };
+    fprintf(stderr, "[attn trace] mma: start=0 prologue issued=%lld  end(sync)=%lld\n", rel(1), rel(2));
+    const int nkv = (T + BKV - 1) / BKV;
+    for (int j = 0; j < nkv && j < 16; ++j) {
+      fprintf(stderr, "[attn trace] j=%d mma t0: waitP %lld->%lld issued %lld | t1: waitP %lld->%lld issued %lld\n", j,
+              rel(64 + j * 16 + 0), rel(64 + j * 16 + 1), rel(64 + j * 16 + 3),
+              rel(64 + j * 16 + 4), rel(64 + j * 16 + 5), rel(64 + j * 16 + 7));
+      for (int t = 0; t < 2; ++t) {
+        const int b0 = 512 + j * 32 + t * 16;
+        fprintf(stderr, "[attn trace]   sm%d: waitS %lld->%lld ld %lld max %lld exp %lld waitO %lld corr+sts %lld arrive %lld\n",
+                t, rel(b0 + 0), rel(b0 + 1), rel(b0 + 2), rel(b0 + 3), rel(b0 + 4), rel(b0 + 5), rel(b0 + 6),
+                rel(b0 + 7));
+      }
+    }
+    for (int t = 0; t < 2; ++t)
+      fprintf(stderr, "[attn trace] epilogue t%d: waitO %lld->%lld done %lld\n", t, rel(32 + t * 4), rel(32 + t * 4 + 1),
+              rel(32 + t * 4 + 2));
+    return cudaGetLastError();
+  }
+  cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)SMEM_ALLOC);
   if (e != cudaSuccess) return e;
-  const int npairs = (T + 2 * BM - 1) / (2 * BM);
-  const long grid = (long)B * npairs;
-  if (grid > 0x7fffffffL) return cudaErrorInvalidValue;
-  attn_tc_kernel<<<(unsigned)grid, NTHREADS, SMEM_ALLOC, s>>>(tq, tk, tv, o, lengths, T, npairs);
+  attn_tc_kernel<false><<<(unsigned)grid, NTHREADS, SMEM_ALLOC, s>>>(tq, tk, tv, to, o, lengths, T, npairs, n_items, nullptr);
   return cudaGetLastError();
 }
 

@@ -40,16 +40,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (mbarrier.try_wait may suspend the thread for a system-defined time).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  bool reported = false;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
+    const long long dt = clock64() - t0;
+    if (dt > 2000000000LL && !reported) {   // ~1 s: report every blocked waiter ...
       printf("vadb: mbarrier wait timeout (tag %d, block %d, thread %d, parity %u)\n", tag,
              (int)blockIdx.x, (int)threadIdx.x, parity);
-      __trap();
+      reported = true;
     }
+    if (dt > 5000000000LL) __trap();        // ... then fail the launch instead of hanging the GPU
   }
 }
 
@@ -141,6 +156,45 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the descriptors passed as 32-bit halves: lo = (addr >> 4) | (LBO >> 4) << 16 differs per
+// operand, hi (SBO, version, swizzle mode) is shared.  Keeps the per-MMA issue cost to an add or two.
+__device__ __forceinline__ void umma_ss_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 rows on the 128 TMEM lanes, K = 16 bf16
+// packed two per 32-bit column -> 8 columns) is read from tensor memory, so it costs no shared-memory
+// bandwidth.  Used for P V with P written by the softmax threads straight into TMEM.
+__device__ __forceinline__ void umma_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// hi word of a 128B-swizzled descriptor with SBO = 1024 B: SBO>>4 at [0,14), version 1 at bit 14,
+// layout SWIZZLE_128B (2) at [29,32)
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+// One lane of a converged warp; the compiler treats the guarded code as warp-uniform.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+               : "=r"(pred));
+  return pred != 0;
+}
+
 // Arrive on an mbarrier when all tcgen05 ops previously issued by this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -192,6 +246,13 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Same, but pinned in program order relative to other volatile asm (named barriers): used where the
+// exponentials of two warpgroups are deliberately serialised on the SFU.
+__device__ __forceinline__ float fast_exp2_pinned(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
