@@ -451,15 +451,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 
 }  // namespace
 
+CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank, void* base,
+                      const cuuint64_t* gdim, const cuuint64_t* gstride, const cuuint32_t* box,
+                      const cuuint32_t* estr, CUtensorMapSwizzle swz) {
+  typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+      return CUDA_ERROR_NOT_FOUND;
+    fn = reinterpret_cast<Fn>(p);
+  }
+  return fn(map, dt, rank, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
 CUresult make_tmap_bt128(CUtensorMap* map, const void* base, int B, int T, int box_rows) {
   cuuint64_t gdim[3] = {128, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t gstride[2] = {256, (cuuint64_t)T * 256};
   cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  return cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim,
-                                gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box,
+                      estr, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o, const int32_t* lengths,

@@ -12,10 +12,11 @@
 // CTA (persistent over 128-row tiles, weights loaded once):
 //   warp 0      TMA producer: W (once), A k-chunks when A is bf16 in global memory
 //   warp 1      MMA issuer (one elected thread), TMEM allocator
-//   warps 2-5   LayerNorm producers (A = fp32 residual stream): coalesced loads, warp-shuffle row
-//               statistics, bf16 into the 128B-swizzled UMMA operand layout
-//   warps 6-9   epilogue: tcgen05.ld accumulators -> bias/ReLU/residual -> swizzled staging tile ->
-//               TMA store (full-line writes); one thread per row
+//   warps 2-5   A producers (A = fp32 residual stream through LayerNorm, or raw feature rows for the
+//               front end): coalesced loads prefetched one batch ahead, warp-shuffle row statistics,
+//               bf16 into the 128B-swizzled UMMA operand layout
+//   warps 6-13  epilogue: tcgen05.ld accumulators -> bias/ReLU/residual/positional encoding -> per-warp
+//               swizzled staging slab -> per-warp TMA store (full-line writes, no cross-warp barrier)
 // Accumulators: four 128-column TMEM slots used as a ring over (tile, n-block) jobs, so the MMAs of
 // the next job overlap the epilogue of the previous one.
 #include "tc_common.cuh"
@@ -26,41 +27,51 @@ namespace {
 
 using namespace tc;
 
-constexpr int NTHREADS = 320;
+constexpr int NTHREADS = 448;          // TMA + MMA + 4 producer warps + 8 epilogue warps
+constexpr int N_EPI_WARPS = 8;
 constexpr uint32_t BLK_BYTES = 128 * 128 * 2;     // [128 x 128] bf16 block = two SW128 halves of 16 KB
 constexpr uint32_t HALF_BYTES = 128 * 128;        // [128 rows x 64 k] bf16
-constexpr uint32_t STG_BYTES = 128 * 128;         // staging tile: 128 rows x 128 B
+constexpr uint32_t STG_BYTES = 32 * 128;          // per-warp staging: 32 rows x 128 B
 constexpr uint32_t IDESC = idesc_bf16(128, 128, 0, 0);
 
 enum { BAR_WFULL = 0, BAR_AFULL = 1, BAR_AEMPTY = 4, BAR_ACCFULL = 7, BAR_ACCEMPTY = 11, BAR_COUNT = 15 };
 
 struct GemmTcParams {
-  int M, N, K;              // N, K multiples of 128; N <= 512; N*K <= 65536
-  int n_a_stages;           // 2 or 3
-  int ln;                   // 1: A = fp32 [M,128] through LayerNorm (K == 128)
-  const float* a_f32;       // LN mode source
+  int M, N, K;              // N multiple of 128, <= 512; K (padded) multiple of 128; N*K <= 65536
+  int n_a_stages;           // 1..3
+  int n_stg;                // staging slabs per epilogue warp (1 or 2)
+  int prod;                 // 0: A is bf16 in global memory (TMA); 1: A = LayerNorm(fp32 rows, K == 128);
+                            // 2: A = fp32/bf16 rows of a_cols <= 128 columns, converted and zero-padded
+  const void* a_src;        // producer modes: source rows
+  int a_cols;               // producer mode 2: valid columns (multiple of 4)
+  int a_is_bf16;            // producer mode 2: source element type
+  int win_W, win_half, win_jump;   // producer mode 2: window gather (vad/predictor.py:182-218) when win_W > 0
   const float* ln_g;
   const float* ln_b;
   const float* bias;        // [N]
   int relu;
-  const float* residual;    // fp32 [M, 128] (N == 128) or nullptr
+  const float* residual;    // fp32 [*, 128] added in the epilogue (N == 128) or nullptr
+  int res_mod;              // > 0: residual row = output row % res_mod (positional-encoding table)
   int out_f32;              // 1: fp32 output [M, N]; 0: bf16
   int out_split;            // bf16 outputs: columns [j*128, j*128+128) -> out map j when split (q,k,v)
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ long window_src_row(long m, int W, int half, int jump) {
+  // vad/predictor.py:186-199: rel = [-half..0) step jump, 0, [1..half] step jump
+  const long i = m / W;
+  const int k = (int)(m - i * W);
+  const int nl = (half + jump - 1) / jump;
+  const int rel = (k < nl) ? (-half + k * jump) : (k == nl ? 0 : 1 + (k - nl - 1) * jump);
+  return half + i + rel;
+}
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_a,
@@ -74,7 +85,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   const uint32_t off_w = 0;
   const uint32_t off_a = off_w + (uint32_t)(NB * KC) * BLK_BYTES;
   const uint32_t off_stg = off_a + (uint32_t)p.n_a_stages * BLK_BYTES;
-  const uint32_t off_bar = off_stg + 2 * STG_BYTES;
+  const uint32_t off_bar = off_stg + (uint32_t)p.n_stg * N_EPI_WARPS * STG_BYTES;
   const uint32_t bar0 = smem_base + off_bar;
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + off_bar + 8 * BAR_COUNT);
@@ -86,18 +97,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   if (threadIdx.x == 0) {
     mbar_init(BAR(BAR_WFULL), 1);
     for (int s = 0; s < 3; ++s) {
-      mbar_init(BAR(BAR_AFULL + s), p.ln ? 128 : 1);
+      mbar_init(BAR(BAR_AFULL + s), p.prod ? 4 : 1);      // one arrival per producer warp / TMA tx
       mbar_init(BAR(BAR_AEMPTY + s), 1);
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(BAR(BAR_ACCFULL + s), 1);
-      mbar_init(BAR(BAR_ACCEMPTY + s), 128);
+      mbar_init(BAR(BAR_ACCEMPTY + s), N_EPI_WARPS);
     }
     mbar_fence_init();
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_w);
-    if (!p.ln) tma_prefetch_desc(&tm_a);
+    if (!p.prod) tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_o0);
   }
   if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
@@ -115,7 +126,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
           for (int hf = 0; hf < 2; ++hf)
             tma_load_2d(smem_base + off_w + (uint32_t)(nb * KC + kc) * BLK_BYTES + hf * HALF_BYTES, &tm_w,
                         BAR(BAR_WFULL), kc * 128 + hf * 64, nb * 128);
-      if (!p.ln) {
+      if (!p.prod) {
         int ac = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
           for (int kc = 0; kc < KC; ++kc, ++ac) {
@@ -129,157 +140,228 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
-      mbar_wait(BAR(BAR_WFULL), 0, 12);
-      int job = 0, ac0 = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ac0 += KC) {
-        for (int nb = 0; nb < NB; ++nb, ++job) {
-          const int slot = job & 3;
-          mbar_wait(BAR(BAR_ACCEMPTY + slot), ((job >> 2) & 1) ^ 1, 13);
+    // ======================= MMA issuer (whole warp walks, one elected lane issues) =======================
+    mbar_wait(BAR(BAR_WFULL), 0, 12);
+    const uint32_t a_lo0 = desc_lo(smem_base + off_a, 16);
+    const uint32_t w_lo0 = desc_lo(smem_base + off_w, 16);
+    int job = 0, ac0 = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ac0 += KC) {
+      for (int nb = 0; nb < NB; ++nb, ++job) {
+        const int slot = job & 3;
+        mbar_wait(BAR(BAR_ACCEMPTY + slot), ((job >> 2) & 1) ^ 1, 13);
+        for (int kc = 0; kc < KC; ++kc) {
+          const int ac = ac0 + kc, s = ac % NA;
+          if (nb == 0) mbar_wait(BAR(BAR_AFULL + s), (ac / NA) & 1, 14);
           tc_fence_after();
-          for (int kc = 0; kc < KC; ++kc) {
-            const int ac = ac0 + kc, s = ac % NA;
-            if (nb == 0) { mbar_wait(BAR(BAR_AFULL + s), (ac / NA) & 1, 14); tc_fence_after(); }
-            const uint32_t a_addr = smem_base + off_a + s * BLK_BYTES;
-            const uint32_t w_addr = smem_base + off_w + (uint32_t)(nb * KC + kc) * BLK_BYTES;
+          if (elect_one()) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)s * (BLK_BYTES >> 4);
+            const uint32_t w_lo = w_lo0 + (uint32_t)(nb * KC + kc) * (BLK_BYTES >> 4);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                umma_ss(tmem_base + slot * 128, desc_kmajor_sw128(a_addr + hf * HALF_BYTES + kk * 32),
-                        desc_kmajor_sw128(w_addr + hf * HALF_BYTES + kk * 32), IDESC,
-                        (kc | hf | kk) != 0);
+                umma_ss_lh(tmem_base + slot * 128, a_lo + hf * (HALF_BYTES >> 4) + kk * 2,
+                           w_lo + hf * (HALF_BYTES >> 4) + kk * 2, DESC_HI_SW128, IDESC,
+                           (kc | hf | kk) != 0 ? 1u : 0u);
             if (nb == NB - 1) umma_commit(BAR(BAR_AEMPTY + s));   // A chunk no longer needed
+            if (kc == KC - 1) umma_commit(BAR(BAR_ACCFULL + slot));
           }
-          umma_commit(BAR(BAR_ACCFULL + slot));
+          __syncwarp();
         }
       }
     }
   } else if (warp < 6) {
-    // ======================= LayerNorm producers (A = LN(fp32 rows)) =======================
-    if (p.ln) {
+    // ======================= A producers: fp32/bf16 rows -> (LayerNorm) -> bf16 UMMA operand ===========
+    if (p.prod) {
       const int pw = warp - 2;
-      const float4 gam = __ldg(reinterpret_cast<const float4*>(p.ln_g) + lane);
-      const float4 bet = __ldg(reinterpret_cast<const float4*>(p.ln_b) + lane);
+      float4 gam = make_float4(1.f, 1.f, 1.f, 1.f), bet = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.prod == 1) {
+        gam = __ldg(reinterpret_cast<const float4*>(p.ln_g) + lane);
+        bet = __ldg(reinterpret_cast<const float4*>(p.ln_b) + lane);
+      }
+      const int cols = (p.prod == 1) ? 128 : p.a_cols;
+      const bool lane_ok = lane * 4 < cols;
+      const bool src_bf16 = p.prod == 2 && p.a_is_bf16;
+      // raw (unconverted) row fragment: 4 fp32, or 4 bf16 in .x/.y -- converted only when consumed, so
+      // the loads issued one batch ahead really stay in flight
+      auto load_row = [&](long row) -> float4 {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < p.M && lane_ok) {
+          long src = row;
+          if (p.win_W > 0) src = window_src_row(row, p.win_W, p.win_half, p.win_jump);
+          if (src_bf16) {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p.a_src) + src * cols) + lane);
+            v.x = __uint_as_float(raw.x); v.y = __uint_as_float(raw.y);
+          } else {
+            v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.a_src) + src * cols) + lane);
+          }
+        }
+        return v;
+      };
       int n = 0;
+      const int chunk = (lane & 15) >> 1, sub = (lane & 1) * 8;
+      float4 x[8], xn[8];
+      {
+        const long row0 = (long)blockIdx.x * 128 + pw * 32;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xn[u] = (blockIdx.x < n_tiles) ? load_row(row0 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
         const int s = n % NA;
         mbar_wait(BAR(BAR_AEMPTY + s), ((n / NA) & 1) ^ 1, 15);
         unsigned char* a_half = smem_gen + off_a + s * BLK_BYTES + (lane >> 4) * HALF_BYTES;
-        const int chunk = (lane & 15) >> 1, sub = (lane & 1) * 8;
 #pragma unroll 1
         for (int r0 = 0; r0 < 32; r0 += 8) {
-          float4 x[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const long row = (long)tile * 128 + pw * 32 + r0 + u;
-            x[u] = (row < p.M) ? __ldg(reinterpret_cast<const float4*>(p.a_f32 + row * 128) + lane)
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int u = 0; u < 8; ++u) x[u] = xn[u];
+          {  // prefetch the next batch of 8 rows (next tile's first batch after the last one)
+            const bool last = r0 == 24;
+            const long nrow0 = last ? ((long)(tile + gridDim.x) * 128 + pw * 32) : ((long)tile * 128 + pw * 32 + r0 + 8);
+            const bool any = !last || (tile + (int)gridDim.x < n_tiles);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xn[u] = any ? load_row(nrow0 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            float sum = (x[u].x + x[u].y) + (x[u].z + x[u].w);
+            float y0 = x[u].x, y1 = x[u].y, y2 = x[u].z, y3 = x[u].w;
+            if (src_bf16) {
+              const uint32_t r0b = __float_as_uint(x[u].x), r1b = __float_as_uint(x[u].y);
+              y0 = __uint_as_float(r0b << 16); y1 = __uint_as_float(r0b & 0xFFFF0000u);
+              y2 = __uint_as_float(r1b << 16); y3 = __uint_as_float(r1b & 0xFFFF0000u);
+            }
+            if (p.prod == 1) {
+              float sum = (y0 + y1) + (y2 + y3);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            const float mean = sum * (1.0f / 128.0f);
-            const float dx = x[u].x - mean, dy = x[u].y - mean, dz = x[u].z - mean, dw = x[u].w - mean;
-            float sq = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+              for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+              const float mean = sum * (1.0f / 128.0f);
+              const float dx = y0 - mean, dy = y1 - mean, dz = y2 - mean, dw = y3 - mean;
+              float sq = (dx * dx + dy * dy) + (dz * dz + dw * dw);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-            const float rstd = rsqrtf(sq * (1.0f / 128.0f) + LN_EPS);
+              for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+              const float rstd = rsqrtf(sq * (1.0f / 128.0f) + LN_EPS);
+              y0 = dx * rstd * gam.x + bet.x; y1 = dy * rstd * gam.y + bet.y;
+              y2 = dz * rstd * gam.z + bet.z; y3 = dw * rstd * gam.w + bet.w;
+            }
             const int r = pw * 32 + r0 + u;
             uint2 pk;
-            pk.x = pack_bf16(dx * rstd * gam.x + bet.x, dy * rstd * gam.y + bet.y);
-            pk.y = pack_bf16(dz * rstd * gam.z + bet.z, dw * rstd * gam.w + bet.w);
+            pk.x = pack_bf16(y0, y1);
+            pk.y = pack_bf16(y2, y3);
             *reinterpret_cast<uint2*>(a_half + sw128_offset(r, chunk) + sub) = pk;
           }
         }
         fence_proxy_async_smem();
-        mbar_arrive(BAR(BAR_AFULL + s));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(BAR_AFULL + s));
       }
     }
   } else {
-    // ======================= epilogue =======================
-    const int ew = warp - 6;                         // 0..3
+    // ======================= epilogue: 8 warps, two per TMEM lane quarter =======================
+    // Warp (q, hsel) owns rows 32q..32q+31 and columns [64 hsel, 64 hsel + 64) of every 128-column
+    // accumulator slot; it stages its 32-row slab in its own 4 KB buffer and issues its own TMA store,
+    // so the epilogue needs no cross-warp barrier.
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int hsel = (warp - 6) >> 2;                // which column half of the slot
     const int row = q * 32 + lane;                   // row inside the tile
-    const int et = threadIdx.x - 6 * 32;             // 0..127
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    unsigned char* stg = smem_gen + off_stg;
+    const uint32_t stg_off0 = off_stg + (uint32_t)(warp - 6) * p.n_stg * STG_BYTES;
     int job = 0, unit = 0;
+    const bool dbl = p.n_stg == 2;
+    // with two slabs a store may still be reading the other one: wait only for the store before last
+    auto wait_slab_free = [&]() {
+      if (lane == 0) {
+        if (dbl) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else tma_store_wait_read0();
+      }
+      __syncwarp();
+    };
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long grow = (long)tile * 128 + row;
+      const bool row_ok = grow < p.M;
+      const float* res_row = nullptr;
+      if (p.residual) res_row = p.residual + (p.res_mod > 0 ? (grow % p.res_mod) : grow) * 128 + hsel * 64;
+      // residual prefetch for the first 32-column chunk (independent of the accumulator)
+      float4 rcur[8], rnext[8];
+      if (p.residual) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          rnext[i] = row_ok ? reinterpret_cast<const float4*>(res_row)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       for (int nb = 0; nb < NB; ++nb, ++job) {
         const int slot = job & 3;
         mbar_wait(BAR(BAR_ACCFULL + slot), (job >> 2) & 1, 16);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + lane_addr + slot * 128;
+        const uint32_t tacc = tmem_base + lane_addr + slot * 128 + hsel * 64;
         const CUtensorMap* om = (p.out_split && nb == 1) ? &tm_o1 : (p.out_split && nb == 2) ? &tm_o2 : &tm_o0;
-        const int ocol0 = p.out_split ? 0 : nb * 128;
-#pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
-          uint32_t v[32];
-          tmem_ld32(tacc + cb * 32, v);
-          tmem_ld_wait();
-          if (cb == 3) { tc_fence_before(); mbar_arrive(BAR(BAR_ACCEMPTY + slot)); }   // slot drained
-          float f[32];
-          {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + nb * 128 + cb * 32);
+        const int ocol0 = (p.out_split ? 0 : nb * 128) + hsel * 64;
+        uint32_t v[2][32];
+        tmem_ld32(tacc, v[0]);
+        tmem_ld32(tacc + 32, v[1]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(BAR_ACCEMPTY + slot));   // this warp's share of the slot is drained
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b4 = __ldg(bp + i);               // warp-uniform address: one transaction
-              f[4 * i] = __uint_as_float(v[4 * i]) + b4.x;
-              f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
-              f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
-              f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
-            }
+        for (int cb = 0; cb < 2; ++cb) {
+          float f[32];
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + nb * 128 + hsel * 64 + cb * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b4 = __ldg(bp + i);                  // warp-uniform address: one transaction
+            f[4 * i] = __uint_as_float(v[cb][4 * i]) + b4.x;
+            f[4 * i + 1] = __uint_as_float(v[cb][4 * i + 1]) + b4.y;
+            f[4 * i + 2] = __uint_as_float(v[cb][4 * i + 2]) + b4.z;
+            f[4 * i + 3] = __uint_as_float(v[cb][4 * i + 3]) + b4.w;
           }
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
           }
-          if (p.residual && grow < p.M) {
-            const float4* rp = reinterpret_cast<const float4*>(p.residual + grow * 128 + cb * 32);
+          if (p.residual) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
+            if (cb == 0) {                                     // prefetch the second chunk of this row
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                rnext[i] = row_ok ? reinterpret_cast<const float4*>(res_row + 32)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 r4 = rp[i];   // plain load: the buffer is also this kernel's output
-              f[4 * i] += r4.x; f[4 * i + 1] += r4.y; f[4 * i + 2] += r4.z; f[4 * i + 3] += r4.w;
+              f[4 * i] += rcur[i].x; f[4 * i + 1] += rcur[i].y; f[4 * i + 2] += rcur[i].z; f[4 * i + 3] += rcur[i].w;
             }
           }
           if (p.out_f32) {
             // one store unit = 32 fp32 columns (128 B per row)
-            unsigned char* sb = stg + (unit & 1) * STG_BYTES;
-            if (et == 0) tma_store_wait_read<1>();
-            named_bar_sync(1, 128);
+            const uint32_t so = stg_off0 + (dbl ? (unit & 1) * STG_BYTES : 0);
+            unsigned char* stg = smem_gen + so;
+            const uint32_t stg_u32 = smem_base + so;
+            wait_slab_free();
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-              *reinterpret_cast<float4*>(sb + sw128_offset(row, c)) =
+              *reinterpret_cast<float4*>(stg + sw128_offset(lane, c)) =
                   make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
             fence_proxy_async_smem();
-            named_bar_sync(1, 128);
-            if (et == 0) {
-              tma_store_2d(om, smem_u32(sb), ocol0 + cb * 32, tile * 128);
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(om, stg_u32, ocol0 + cb * 32, tile * 128 + q * 32);
               tma_store_commit();
             }
             ++unit;
           } else {
-            // one store unit = 64 bf16 columns (128 B per row) = two 32-column accumulator chunks
-            unsigned char* sb = stg + (unit & 1) * STG_BYTES;
-            if ((cb & 1) == 0) {
-              if (et == 0) tma_store_wait_read<1>();
-              named_bar_sync(1, 128);
-            }
+            // one store unit = 64 bf16 columns (128 B per row) = both 32-column chunks
+            const uint32_t so = stg_off0 + (dbl ? (unit & 1) * STG_BYTES : 0);
+            unsigned char* stg = smem_gen + so;
+            const uint32_t stg_u32 = smem_base + so;
+            if (cb == 0) wait_slab_free();
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-              *reinterpret_cast<uint4*>(sb + sw128_offset(row, (cb & 1) * 4 + c)) =
+              *reinterpret_cast<uint4*>(stg + sw128_offset(lane, cb * 4 + c)) =
                   make_uint4(pack_bf16(f[8 * c], f[8 * c + 1]), pack_bf16(f[8 * c + 2], f[8 * c + 3]),
                              pack_bf16(f[8 * c + 4], f[8 * c + 5]), pack_bf16(f[8 * c + 6], f[8 * c + 7]));
-            if (cb & 1) {
+            if (cb == 1) {
               fence_proxy_async_smem();
-              named_bar_sync(1, 128);
-              if (et == 0) {
-                tma_store_2d(om, smem_u32(sb), ocol0 + (cb >> 1) * 64, tile * 128);
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(om, stg_u32, ocol0, tile * 128 + q * 32);
                 tma_store_commit();
               }
               ++unit;
@@ -288,8 +370,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         }
       }
     }
-    if (et == 0) tma_store_wait_all();
-    (void)ew;
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -306,9 +387,7 @@ CUresult make_tmap_2d(CUtensorMap* map, const void* base, CUtensorMapDataType dt
   cuuint64_t gstride[1] = {(cuuint64_t)cols * esz};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  return cuTensorMapEncodeTiled(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return encode_tiled(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 }  // namespace
@@ -320,28 +399,38 @@ cudaError_t launch_gemm_tc(const GemmTcArgs& a, int num_sms, cudaStream_t s, std
   if ((a.N > 128) && (a.K > 128)) return bad("N > 128 requires K == 128");
   if (a.ln_g && a.K != 128) return bad("LayerNorm prologue needs K == 128");
   if (a.residual && a.N != 128) return bad("residual needs N == 128");
+  if (a.a_rows && (a.K != 128 || a.a_cols <= 0 || a.a_cols > 128 || a.a_cols % 4)) return bad("bad a_cols");
   GemmTcParams p = {};
   p.M = a.M; p.N = a.N; p.K = a.K;
-  p.ln = a.ln_g != nullptr; p.a_f32 = a.a_f32; p.ln_g = a.ln_g; p.ln_b = a.ln_b;
-  p.bias = a.bias; p.relu = a.relu; p.residual = a.residual;
+  p.prod = a.ln_g ? 1 : (a.a_rows ? 2 : 0);
+  p.a_src = a.ln_g ? (const void*)a.a_f32 : a.a_rows;
+  p.a_cols = a.a_cols; p.a_is_bf16 = a.a_rows_bf16;
+  p.win_W = a.win_W; p.win_half = a.win_half; p.win_jump = a.win_jump;
+  p.ln_g = a.ln_g; p.ln_b = a.ln_b;
+  p.bias = a.bias; p.relu = a.relu; p.residual = a.residual; p.res_mod = a.res_mod;
   p.out_f32 = a.out_f32; p.out_split = a.out[1] != nullptr;
   const uint32_t w_bytes = (uint32_t)(a.N / 128) * (a.K / 128) * BLK_BYTES;
-  const uint32_t fixed = w_bytes + 2 * STG_BYTES + 256 + 1024;
-  p.n_a_stages = (fixed + 3 * BLK_BYTES <= 232448u) ? 3 : 2;
-  const uint32_t smem = fixed + p.n_a_stages * BLK_BYTES;
-  if (smem > 232448u) return bad("shared memory budget exceeded");
+  // shared-memory plan: resident W + A ring + per-warp staging slabs.  Prefer two staging slabs per
+  // warp (a TMA store takes ~1 us to drain a slab) with at least two A stages; fall back to one slab.
+  const uint32_t LIMIT = 232448u, misc = 256 + 1024;
+  const uint32_t stg1 = N_EPI_WARPS * STG_BYTES;
+  p.n_stg = (w_bytes + 2 * BLK_BYTES + 2 * stg1 + misc <= LIMIT) ? 2 : 1;
+  p.n_a_stages = 1;
+  while (p.n_a_stages < 3 && w_bytes + (p.n_a_stages + 1) * BLK_BYTES + p.n_stg * stg1 + misc <= LIMIT) ++p.n_a_stages;
+  const uint32_t smem = w_bytes + p.n_a_stages * BLK_BYTES + p.n_stg * stg1 + misc;
+  if (smem > LIMIT) return bad("shared memory budget exceeded");
 
   CUtensorMap tw, ta, to[3];
   CUresult r = make_tmap_2d(&tw, a.w_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.K, 64, 128);
   if (r == CUDA_SUCCESS)
-    r = p.ln ? CUDA_SUCCESS
-             : make_tmap_2d(&ta, a.a_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.K, 64, 128);
-  if (p.ln) ta = tw;
+    r = p.prod ? CUDA_SUCCESS
+               : make_tmap_2d(&ta, a.a_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.K, 64, 128);
+  if (p.prod) ta = tw;
   const int ocols = p.out_split ? 128 : a.N;
   for (int j = 0; j < 3 && r == CUDA_SUCCESS; ++j) {
     void* optr = a.out[j] ? a.out[j] : a.out[0];
-    r = a.out_f32 ? make_tmap_2d(&to[j], optr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, ocols, 32, 128)
-                  : make_tmap_2d(&to[j], optr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, ocols, 64, 128);
+    r = a.out_f32 ? make_tmap_2d(&to[j], optr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, ocols, 32, 32)
+                  : make_tmap_2d(&to[j], optr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, ocols, 64, 32);
   }
   if (r != CUDA_SUCCESS) {
     if (err) *err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")";

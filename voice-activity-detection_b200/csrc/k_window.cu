@@ -50,7 +50,21 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restric
     for (size_t j = n & ~(size_t)3; j < n; ++j) out[j] = __float2bfloat16_rn(in[j]);
 }
 
+// [rows, cols] fp32 -> [rows, 128] bf16, zero-padded columns (front-end weight for the tensor-core path)
+__global__ void pad_rows_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int rows, int cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * 128) {
+    const int r = i >> 7, c = i & 127;
+    out[i] = __float2bfloat16_rn(c < cols ? in[(long)r * cols + c] : 0.f);
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_pad_rows_bf16(const float* in, bf16* out, int rows, int cols, cudaStream_t s) {
+  pad_rows_bf16_kernel<<<(rows * 128 + 255) / 256, 256, 0, s>>>(in, out, rows, cols);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_boost(const float* prob_nW, int L, int half, int jump, int W, float* probs_LW,
                          float* mean_L, cudaStream_t s) {

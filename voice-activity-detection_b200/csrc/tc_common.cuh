@@ -263,7 +263,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 }  // namespace tc
 
-// Host side: bf16 [B, T, 128] tensor viewed as 3-D {128, T, B}; box {64 cols, box_rows, 1},
+// Host side.  cuTensorMapEncodeTiled is resolved through the runtime (cudaGetDriverEntryPoint) so that
+// libvadb200.so has no link-time dependency on libcuda.so.1 and still loads on a machine without a driver.
+CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank, void* base,
+                      const cuuint64_t* gdim, const cuuint64_t* gstride, const cuuint32_t* box,
+                      const cuuint32_t* estr, CUtensorMapSwizzle swz);
+
+// bf16 [B, T, 128] tensor viewed as 3-D {128, T, B}; box {64 cols, box_rows, 1},
 // 128-byte swizzle, out-of-bounds rows (t >= T) read as zeros.
 CUresult make_tmap_bt128(CUtensorMap* map, const void* base, int B, int T, int box_rows);
 

@@ -56,6 +56,7 @@ struct vadb_handle {
   bf16* wo_bf = nullptr;     // [L][128*128]
   bf16* w1_bf = nullptr;     // [L][512*128]
   bf16* w2_bf = nullptr;     // [L][128*512]
+  bf16* win_bf = nullptr;    // [128, 128] front-end weight, columns >= F zero (tensor-core front end)
 
   float* pe = nullptr;       // [pe_T, 128] = PE / sqrt(d)
   int pe_T = 0;
@@ -69,7 +70,8 @@ struct vadb_handle {
   float* ws_prob = nullptr;
 
   // host-call staging
-  cudaStream_t own_stream = nullptr;
+  cudaStream_t own_stream = nullptr, own_stream2 = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   void* pin_in = nullptr; size_t pin_in_bytes = 0;
   void* pin_out = nullptr; size_t pin_out_bytes = 0;
   void* dev_in = nullptr; size_t dev_in_bytes = 0;
@@ -272,6 +274,30 @@ int run_encoder(vadb_handle* h, const int32_t* lengths, int Bc, int T, float* pr
   return VADB_OK;
 }
 
+// h = x W_in^T + b_in + PE/sqrt(d) (self_attention.py:13-14, transformer.py:401), optionally with the
+// predictor's window gather folded into the A-row index.  bf16 mode with F <= 128 (F % 4 == 0): tensor
+// cores; otherwise the fp32 CUDA-core kernel.
+int front_end(vadb_handle* h, const void* x, int x_is_bf16, int M, int pe_T, int win_W, int win_half,
+              int win_jump, cudaStream_t s) {
+  const int F = h->cfg.feature_size;
+  if (is_bf16_mode(h) && F <= D && F % 4 == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0) {
+    GemmTcArgs g = {};
+    g.M = M; g.N = D; g.K = D; g.w_bf16 = h->win_bf;
+    g.a_rows = x; g.a_cols = F; g.a_rows_bf16 = x_is_bf16;
+    g.win_W = win_W; g.win_half = win_half; g.win_jump = win_jump;
+    g.bias = h->w32 + h->lay.b_in; g.residual = h->pe; g.res_mod = pe_T;
+    g.out_f32 = 1; g.out[0] = h->ws_h;
+    return gemm_tc(h, g, s);
+  }
+  GemmArgs g = {};
+  g.A = x; g.a_is_bf16 = x_is_bf16;
+  g.W = h->w32 + h->lay.w_in; g.bias = h->w32 + h->lay.b_in;
+  g.M = M; g.N = D; g.K = F; g.pe = h->pe; g.pe_T = pe_T;
+  g.win_W = win_W; g.win_half = win_half; g.win_jump = win_jump;
+  g.out[0] = h->ws_h; g.out_split = D;
+  return gemm(h, g, s);
+}
+
 int check_ready(vadb_handle* h) {
   if (!h) return VADB_E_INVALID;
   if (!h->loaded) return fail(h, VADB_E_STATE, "weights not loaded (call vadb_load_weights first)");
@@ -335,6 +361,11 @@ int vadb_create(vadb_handle** out, const vadb_config* cfg, int device) {
   h->num_sms = prop.multiProcessorCount;
   DeviceGuard dg(device);
   e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream2, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete h; return fail(nullptr, VADB_E_CUDA, m); }
   *out = h;
   return VADB_OK;
@@ -345,7 +376,7 @@ void vadb_destroy(vadb_handle* h) {
   DeviceGuard dg(h->device);
   cudaDeviceSynchronize();
   free_dev(h->w32); free_dev(h->wqkv); free_dev(h->bqkv);
-  free_dev(h->wqkv_bf); free_dev(h->wo_bf); free_dev(h->w1_bf); free_dev(h->w2_bf);
+  free_dev(h->wqkv_bf); free_dev(h->wo_bf); free_dev(h->w1_bf); free_dev(h->w2_bf); free_dev(h->win_bf);
   free_dev(h->pe);
   free_dev(h->ws_h); free_dev(h->ws_q); free_dev(h->ws_k); free_dev(h->ws_v); free_dev(h->ws_o);
   free_dev(h->ws_hid); free_dev(h->ws_prob);
@@ -356,6 +387,11 @@ void vadb_destroy(vadb_handle* h) {
   if (h->dev_len) cudaFree(h->dev_len);
   if (h->win_prob) cudaFree(h->win_prob);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->own_stream2) cudaStreamDestroy(h->own_stream2);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+    if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+  }
   delete h;
 }
 
@@ -377,9 +413,12 @@ int vadb_load_weights(vadb_handle* h, const float* blob, size_t count, int on_de
     CU_TRY(h, cudaMalloc(&h->wo_bf, (size_t)L * D * D * sizeof(bf16)));
     CU_TRY(h, cudaMalloc(&h->w1_bf, (size_t)L * DFF * D * sizeof(bf16)));
     CU_TRY(h, cudaMalloc(&h->w2_bf, (size_t)L * D * DFF * sizeof(bf16)));
+    CU_TRY(h, cudaMalloc(&h->win_bf, (size_t)D * D * sizeof(bf16)));
   }
   CU_TRY(h, cudaMemcpyAsync(h->w32, blob, count * sizeof(float),
                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  if (h->cfg.feature_size <= D)
+    CU_TRY(h, launch_pad_rows_bf16(h->w32 + h->lay.w_in, h->win_bf, D, h->cfg.feature_size, s));
   for (int l = 0; l < L; ++l) {
     const LayerOffsets& lo = h->lay.layers[l];
     const size_t srcw[3] = {lo.wq, lo.wk, lo.wv}, srcb[3] = {lo.bq, lo.bk, lo.bv};
@@ -433,13 +472,8 @@ int vadb_forward(vadb_handle* h, const void* x, int x_dtype, const int32_t* leng
   const size_t xsz = x_dtype == VADB_BF16 ? 2 : 4;
   for (int b0 = 0; b0 < B; b0 += cpp) {
     const int Bc = std::min(cpp, B - b0);
-    // h = x W_in^T + b_in + PE[:T]/sqrt(d)     (self_attention.py:13-14, transformer.py:401)
-    GemmArgs g = {};
-    g.A = (const char*)x + (size_t)b0 * T * F * xsz; g.a_is_bf16 = x_dtype == VADB_BF16;
-    g.W = h->w32 + h->lay.w_in; g.bias = h->w32 + h->lay.b_in;
-    g.M = Bc * T; g.N = D; g.K = F; g.pe = h->pe; g.pe_T = T;
-    g.out[0] = h->ws_h; g.out_split = D;
-    if ((rc = gemm(h, g, s))) return rc;
+    if ((rc = front_end(h, (const char*)x + (size_t)b0 * T * F * xsz, x_dtype == VADB_BF16, Bc * T, T, 0, 0, 0, s)))
+      return rc;
     if ((rc = run_encoder(h, lengths ? lengths + b0 : nullptr, Bc, T,
                           prob ? prob + (size_t)b0 * T : nullptr,
                           logp ? logp + (size_t)b0 * T * 2 : nullptr, s)))
@@ -455,38 +489,76 @@ int vadb_forward_host(vadb_handle* h, const float* x, const int32_t* lengths, in
   if (!x || B < 0 || T < 0) return fail(h, VADB_E_INVALID, "bad forward arguments");
   if (B == 0 || T == 0) return VADB_OK;
   DeviceGuard dg(h->device);
-  cudaStream_t s = h->own_stream;
+  // Chunked two-stream pipeline: the H2D copy of clip chunk i+1 overlaps the forward of chunk i
+  // (the reference does one blocking .to(device) per 1000-window chunk, vad/predictor.py:223).
+  cudaStream_t s_copy = h->own_stream, s_comp = h->own_stream2;
   const int F = h->cfg.feature_size;
+  const size_t clip_in = (size_t)T * F * sizeof(float);
+  int C = (int)std::max<size_t>(1, ((size_t)8 << 20) / std::max<size_t>(clip_in, 1));   // ~8 MB chunks
+  C = std::min(C, B);
+  const int n_chunks = (B + C - 1) / C;
   const size_t n = (size_t)B * T;
-  const size_t in_bytes = n * F * sizeof(float);
-  const size_t out_bytes = n * 3 * sizeof(float);      // prob [n] + logp [2n]
-  if ((rc = ensure_bytes(h, &h->pin_in, &h->pin_in_bytes, in_bytes, true))) return rc;
-  if ((rc = ensure_bytes(h, &h->pin_out, &h->pin_out_bytes, out_bytes, true))) return rc;
-  if ((rc = ensure_bytes(h, &h->dev_in, &h->dev_in_bytes, in_bytes, false))) return rc;
-  if ((rc = ensure_bytes(h, &h->dev_out, &h->dev_out_bytes, out_bytes, false))) return rc;
+  auto is_pinned = [](const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
+  const bool in_pinned = is_pinned(x);
+  const bool out_pinned = (!prob || is_pinned(prob)) && (!logp || is_pinned(logp));
+  const size_t chunk_in = (size_t)C * clip_in;
+  if (!in_pinned && (rc = ensure_bytes(h, &h->pin_in, &h->pin_in_bytes, 2 * chunk_in, true))) return rc;
+  if (!out_pinned && (rc = ensure_bytes(h, &h->pin_out, &h->pin_out_bytes, n * 3 * sizeof(float), true))) return rc;
+  if ((rc = ensure_bytes(h, &h->dev_in, &h->dev_in_bytes, 2 * chunk_in, false))) return rc;
+  if ((rc = ensure_bytes(h, &h->dev_out, &h->dev_out_bytes, n * 3 * sizeof(float), false))) return rc;
+  if ((rc = ensure_pe(h, T))) return rc;
+  if ((rc = ensure_workspace(h, (size_t)std::min(C, clips_per_pass(C, T)) * T))) return rc;
   int32_t* dlen = nullptr;
   if (lengths) {
     if ((size_t)B > h->dev_len_n) {
-      if (h->dev_len) cudaFree(h->dev_len);
+      if (h->dev_len) { cudaDeviceSynchronize(); cudaFree(h->dev_len); }
       h->dev_len = nullptr; h->dev_len_n = 0;
       CU_TRY(h, cudaMalloc(&h->dev_len, (size_t)B * sizeof(int32_t)));
       h->dev_len_n = B;
     }
-    CU_TRY(h, cudaMemcpyAsync(h->dev_len, lengths, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    CU_TRY(h, cudaMemcpyAsync(h->dev_len, lengths, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, s_comp));
     dlen = h->dev_len;
   }
-  memcpy(h->pin_in, x, in_bytes);
-  CU_TRY(h, cudaMemcpyAsync(h->dev_in, h->pin_in, in_bytes, cudaMemcpyHostToDevice, s));
   float* dprob = (float*)h->dev_out;
   float* dlogp = dprob + n;
-  if ((rc = vadb_forward(h, h->dev_in, VADB_F32, dlen, B, T, prob ? dprob : nullptr,
-                         logp ? dlogp : nullptr, s)))
-    return rc;
-  if (prob) CU_TRY(h, cudaMemcpyAsync(h->pin_out, dprob, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-  if (logp) CU_TRY(h, cudaMemcpyAsync((float*)h->pin_out + n, dlogp, 2 * n * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CU_TRY(h, cudaStreamSynchronize(s));
-  if (prob) memcpy(prob, h->pin_out, n * sizeof(float));
-  if (logp) memcpy(logp, (float*)h->pin_out + n, 2 * n * sizeof(float));
+  float* hprob = out_pinned ? prob : (float*)h->pin_out;
+  float* hlogp = out_pinned ? logp : (float*)h->pin_out + n;
+  for (int i = 0; i < n_chunks; ++i) {
+    const int b0 = i * C, Bc = std::min(C, B - b0), slot = i & 1;
+    const size_t bytes = (size_t)Bc * clip_in;
+    const char* src = (const char*)x + (size_t)b0 * clip_in;
+    char* dsti = (char*)h->dev_in + (size_t)slot * chunk_in;
+    // device slot free once the forward of chunk i-2 has consumed it
+    if (i >= 2) CU_TRY(h, cudaStreamWaitEvent(s_copy, h->ev_done[slot], 0));
+    if (!in_pinned) {
+      char* stage = (char*)h->pin_in + (size_t)slot * chunk_in;
+      if (i >= 2) CU_TRY(h, cudaEventSynchronize(h->ev_h2d[slot]));   // staging slot copied out
+      memcpy(stage, src, bytes);
+      src = stage;
+    }
+    CU_TRY(h, cudaMemcpyAsync(dsti, src, bytes, cudaMemcpyHostToDevice, s_copy));
+    CU_TRY(h, cudaEventRecord(h->ev_h2d[slot], s_copy));
+    CU_TRY(h, cudaStreamWaitEvent(s_comp, h->ev_h2d[slot], 0));
+    if ((rc = vadb_forward(h, dsti, VADB_F32, dlen ? dlen + b0 : nullptr, Bc, T,
+                           prob ? dprob + (size_t)b0 * T : nullptr,
+                           logp ? dlogp + (size_t)b0 * T * 2 : nullptr, s_comp)))
+      return rc;
+    CU_TRY(h, cudaEventRecord(h->ev_done[slot], s_comp));
+    if (prob) CU_TRY(h, cudaMemcpyAsync(hprob + (size_t)b0 * T, dprob + (size_t)b0 * T, (size_t)Bc * T * sizeof(float),
+                                        cudaMemcpyDeviceToHost, s_comp));
+    if (logp) CU_TRY(h, cudaMemcpyAsync(hlogp + (size_t)b0 * T * 2, dlogp + (size_t)b0 * T * 2,
+                                        (size_t)Bc * T * 2 * sizeof(float), cudaMemcpyDeviceToHost, s_comp));
+  }
+  CU_TRY(h, cudaStreamSynchronize(s_comp));
+  CU_TRY(h, cudaStreamSynchronize(s_copy));
+  if (!out_pinned) {
+    if (prob) memcpy(prob, hprob, n * sizeof(float));
+    if (logp) memcpy(logp, hlogp, 2 * n * sizeof(float));
+  }
   return VADB_OK;
 }
 
@@ -517,12 +589,7 @@ int vadb_predict_probabilities(vadb_handle* h, const float* feat, int L, int hal
       const int nc = std::min(wpp, n - c0);
       // window gather folded into the front-end GEMM's A-row index (vad/predictor.py:182-218);
       // the positional slot of row m is m % W (the window is the model's whole sequence)
-      GemmArgs g = {};
-      g.A = feat + (size_t)c0 * F; g.W = h->w32 + h->lay.w_in; g.bias = h->w32 + h->lay.b_in;
-      g.M = nc * W; g.N = D; g.K = F; g.pe = h->pe; g.pe_T = W;
-      g.win_W = W; g.win_half = half; g.win_jump = jump;
-      g.out[0] = h->ws_h; g.out_split = D;
-      if ((rc = gemm(h, g, s))) return rc;
+      if ((rc = front_end(h, feat + (size_t)c0 * F, 0, nc * W, W, W, half, jump, s))) return rc;
       if ((rc = run_encoder(h, nullptr, nc, W, prob_all + (size_t)c0 * W, nullptr, s))) return rc;
     }
     cudaError_t e = launch_boost(prob_all, L, half, jump, W, probs_LW, mean_L, s);

@@ -71,11 +71,15 @@ struct GemmTcArgs {
   const bf16* w_bf16;      // [N, K]
   const bf16* a_bf16;      // [M, K] (when ln_g == nullptr)
   const float* a_f32;      // [M, 128] fp32 rows through LayerNorm (when ln_g != nullptr)
+  const void* a_rows;      // front end: [*, a_cols] fp32/bf16 feature rows, converted + zero-padded to K = 128
+  int a_cols, a_rows_bf16;
+  int win_W, win_half, win_jump;   // front end: window gather folded into the A-row index (win_W > 0)
   const float* ln_g;
   const float* ln_b;
   const float* bias;       // [N] fp32
   int relu;
   const float* residual;   // fp32 [M,128] or nullptr (may alias out[0])
+  int res_mod;             // > 0: residual row = m % res_mod (positional-encoding table [T,128])
   int out_f32;             // fp32 [M,N] output, else bf16
   void* out[3];            // out[1], out[2] set -> columns split in 128-wide blocks (q, k, v)
 };
@@ -90,6 +94,7 @@ cudaError_t launch_boost(const float* prob_nW, int L, int half, int jump, int W,
                          float* probs_LW, float* mean_L, cudaStream_t s);
 
 // misc element-wise (k_window.cu)
+cudaError_t launch_pad_rows_bf16(const float* in, bf16* out, int rows, int cols, cudaStream_t s);
 cudaError_t launch_f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t s);
 
 }  // namespace vadb
