@@ -296,9 +296,15 @@ def main():
         alg_bytes = 4 * B_PER_GPU * T * D * esz            # read Q,K,V + write O once
         alg_flops = 4 * B_PER_GPU * T * T * D               # QK^T + PV
         achieved = alg_bytes / (ms_attn * 1e-3) / 1e9
+        traffic = None
+        try:    # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (per launch)
+            with open(os.path.join(ROOT, "profiles", "r1_attn_ncu_summary.json")) as f:
+                traffic = json.load(f)["final"]["traffic_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"kernel": "attention (per layer-call, B=256,T=512,d=128)", "bound": "hbm",
                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "peak_source": peak_src, "us_per_launch": ms_attn * 1e3,
+                    "traffic": traffic, "peak_source": peak_src, "us_per_launch": ms_attn * 1e3,
                     "algorithmic_bytes": alg_bytes,
                     "tensor": {"achieved": alg_flops / (ms_attn * 1e-3) / 1e12, "peak": tf_peak,
                                "unit": "TFLOP/s", "frac": alg_flops / (ms_attn * 1e-3) / 1e12 / tf_peak}}
