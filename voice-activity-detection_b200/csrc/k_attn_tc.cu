@@ -8,16 +8,15 @@
 //
 // Persistent CTAs (one per SM) walk a static list of work items; one item = one clip x 256 query rows
 // = two 128-row query tiles:
-//   warp 16     TMA producer: Q (once), a 4-stage ring of 64-key K tiles and a 3-stage ring of V
+//   warp 8      TMA producer: Q (once), a 4-stage ring of 64-key K tiles and a 3-stage ring of V
 //               tiles, all 128B-swizzled
-//   warp 17     MMA issuer (one elected lane): S_t = Q_t K^T and O_t += P_t V via tcgen05.mma with
+//   warp 9      MMA issuer (one elected lane): S_t = Q_t K^T and O_t += P_t V via tcgen05.mma with
 //               accumulators in TMEM -- S double-buffered per query tile (4 x 64 columns),
 //               O 2 x 128 columns.  Q K^T of step j+2 is issued right behind P V of step j, so the
 //               scores of the next step are already in TMEM when a softmax warpgroup finishes a step.
-//   warps 0-15  four softmax warpgroups (query tile t = wg & 1, key-column half c = wg >> 1): two
-//               threads per query row, each owning 32 of the 64 score columns of a step:
-//               tcgen05.ld S -> online softmax (fp32, exp2, lazy rescale of O in TMEM) -> P (bf16
-//               pairs) written back into the S buffer with tcgen05.st
+//   warps 0-3   softmax warpgroup of query tile 0: one thread per query row (TMEM lane),
+//   warps 4-7   softmax warpgroup of query tile 1   tcgen05.ld S -> online softmax (fp32, exp2,
+//               lazy rescale of O in TMEM) -> P (bf16) into swizzled shared memory
 // The two query tiles share every K/V tile and ping-pong on the tensor pipe.
 //
 // Algorithmic traffic per launch: read Q,K,V once + write O once = 4*B*T*128*2 bytes (SURVEY.md
@@ -37,10 +36,9 @@ using namespace tc;
 
 constexpr int BM = 128;          // query rows per tile (UMMA M)
 constexpr int BKV = 64;          // keys per K/V tile
-constexpr int NK = 3;            // K ring depth (K runs two steps ahead of V)
+constexpr int NK = 4;            // K ring depth (K runs two steps ahead of V)
 constexpr int NV = 2;            // V ring depth
-constexpr int NSOFT_WARPS = 16;  // four softmax warpgroups: (query tile t, column half c)
-constexpr int NTHREADS = 32 * (NSOFT_WARPS + 2);   // + producer + MMA
+constexpr int NTHREADS = 320;    // 8 softmax warps + producer + MMA
 
 constexpr uint32_t Q_HALF_BYTES = BM * 128;          // [128 rows x 64 d] bf16 = 16 KB
 constexpr uint32_t Q_TILE_BYTES = 2 * Q_HALF_BYTES;  // two d-halves
@@ -53,8 +51,8 @@ constexpr uint32_t OFF_K = OFF_Q + 2 * Q_TILE_BYTES;
 constexpr uint32_t OFF_V = OFF_K + NK * KV_TILE_BYTES;
 constexpr uint32_t OFF_OST = OFF_V + NV * KV_TILE_BYTES;        // O staging: [tile][d half] x 16 KB
 constexpr uint32_t OFF_BAR = OFF_OST + 4 * P_TILE_BYTES;
-constexpr uint32_t OFF_SCR = OFF_BAR + 256;        // [512] token-pinning sink, [512] row-stat exchange, zero word
-constexpr uint32_t SMEM_BYTES = OFF_SCR + 4096 + 64;
+constexpr uint32_t OFF_SCR = OFF_BAR + 256;        // 256 floats of scratch + one zero word (token pinning)
+constexpr uint32_t SMEM_BYTES = OFF_SCR + 1024 + 64;
 constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;   // slack for 1024-byte alignment
 
 // barrier slots (8 bytes each) at OFF_BAR
@@ -76,7 +74,7 @@ constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units: rescale O only when t
 // second work item into `trace` (VADB_ATTN_TRACE=1); compiled out of the production instantiation.
 #define TR(slot) do { if (TRACE && blockIdx.x == 0 && n_item == 1 && trace) trace[(slot)] = clock64(); } while (0)
 
-struct Item { int b, q0, len, nkv, ntile; };
+struct Item { int b, q0, len, nkv, ntile; bool valid; };
 
 __device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -85,16 +83,27 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 // named barriers: 1/2 = MUFU token (softmax warpgroup 0 / 1 may run its exponentials), 3+t = warpgroup t
-enum { NB_TOKEN0 = 1, NB_TOKEN1 = 2, NB_PAIR = 3 /* +t */, NB_WG = 5 /* +wg */ };
+enum { NB_TOKEN0 = 1, NB_TOKEN1 = 2, NB_WG = 3 };
 
-__device__ __forceinline__ Item get_item(int idx, int npairs, int T, const int32_t* lengths) {
+// Work items.  idx < n_full: one clip x 256 query rows (two tiles sharing K/V).  The pairs of the last,
+// partially filled round are split into single-tile items (idx >= n_full) so that the tail of the launch
+// spreads over twice as many SMs.
+__device__ __forceinline__ Item get_item(int idx, int n_full, int npairs, int T, const int32_t* lengths) {
   Item it;
-  it.b = idx / npairs;
-  it.q0 = (idx % npairs) * 2 * BM;
+  int pair = idx, tile = -1;
+  if (idx >= n_full) { pair = n_full + ((idx - n_full) >> 1); tile = (idx - n_full) & 1; }
+  it.b = pair / npairs;
+  it.q0 = (pair % npairs) * 2 * BM;
+  it.ntile = (it.q0 + BM < T) ? 2 : 1;        // second query tile entirely past T: skip it
+  it.valid = true;
+  if (tile >= 0) {
+    if (tile == 1 && it.ntile == 1) it.valid = false;
+    it.q0 += tile * BM;
+    it.ntile = 1;
+  }
   int len = lengths ? lengths[it.b] : T;
   it.len = min(max(len, 0), T);
   it.nkv = (it.len + BKV - 1) / BKV;
-  it.ntile = (it.q0 + BM < T) ? 2 : 1;        // second query tile entirely past T: skip it
   return it;
 }
 
@@ -103,7 +112,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
                bf16* __restrict__ O, const int32_t* __restrict__ lengths, int T, int npairs, int n_items,
-               long long* trace) {
+               int n_full, long long* trace) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -120,31 +129,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     for (int s = 0; s < NV; ++s) { mbar_init(BAR(B_VFULL + s), 1); mbar_init(BAR(B_VEMPTY + s), 1); }
     for (int i = 0; i < 4; ++i) mbar_init(BAR(B_SFULL + i), 1);
     for (int t = 0; t < 2; ++t) {
-      mbar_init(BAR(B_PFULL + t), 8);          // one arrival per softmax warp of the tile
+      mbar_init(BAR(B_PFULL + t), 4);          // one arrival per softmax warp
       mbar_init(BAR(B_OFULL + t), 1);
     }
     mbar_fence_init();
-    *reinterpret_cast<volatile float*>(smem_gen + OFF_SCR + 4096) = 0.f;
+    *reinterpret_cast<volatile float*>(smem_gen + OFF_SCR + 1024) = 0.f;
   }
-  if (warp == NSOFT_WARPS && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
     tma_prefetch_desc(&tm_o);
   }
-  if (warp == NSOFT_WARPS + 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+  if (warp == 9) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == NSOFT_WARPS) {
+  if (warp == 8) {
     // ======================= TMA producer =======================
     if (lane == 0) {
       int kc = 0, vc = 0, nq = 0;              // K tiles / V tiles / Q loads issued so far
       for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
-        const Item it = get_item(idx, npairs, T, lengths);
-        if (it.nkv == 0) continue;
+        const Item it = get_item(idx, n_full, npairs, T, lengths);
+        if (!it.valid || it.nkv == 0) continue;
         mbar_wait(BAR(B_QEMPTY), (nq & 1) ^ 1, 1);            // every Q K^T of the previous item retired
         mbar_arrive_expect_tx(BAR(B_QFULL), it.ntile * Q_TILE_BYTES);
         for (int t = 0; t < it.ntile; ++t)
@@ -175,7 +184,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         kc += it.nkv; vc += it.nkv;
       }
     }
-  } else if (warp == NSOFT_WARPS + 1) {
+  } else if (warp == 9) {
     // ======================= MMA issuer =======================
     // The whole warp walks the schedule (waits included) and one elected lane issues, so the
     // descriptor arithmetic stays warp-uniform and costs an add or two per MMA.
@@ -208,8 +217,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     int kc = 0, vc = 0, nq = 0, n_item = 0;
     int g[2] = {0, 0};                          // softmax steps issued so far, per query tile
     for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n_item) {
-      const Item it = get_item(idx, npairs, T, lengths);
-      if (it.nkv == 0) continue;
+      const Item it = get_item(idx, n_full, npairs, T, lengths);
+      if (!it.valid || it.nkv == 0) continue;
       const int nkv = it.nkv, ntile = it.ntile;
       TR(0);
       mbar_wait(BAR(B_QFULL), nq & 1, 4);
@@ -262,44 +271,39 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     }
   } else {
     // ======================= softmax warpgroups =======================
-    const int wg = warp >> 2;                      // 0..3
-    const int t = wg & 1;                          // query tile
-    const int ch = wg >> 1;                        // key-column half of every 64-key step
+    const int t = warp >> 2;                       // query tile of this warpgroup
     const int row = (warp & 3) * 32 + lane;        // row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t ts = tmem_base + lane_addr + TM_S + 128 * t;
-    const uint32_t to = tmem_base + lane_addr + TM_O + 128 * t + 64 * ch;   // this thread's 64 O columns
-    unsigned char* ost = smem_gen + OFF_OST + (t * 2 + ch) * P_TILE_BYTES;
-    const uint32_t ost_u32 = smem_base + OFF_OST + (t * 2 + ch) * P_TILE_BYTES;
-    volatile float* sink = reinterpret_cast<volatile float*>(smem_gen + OFF_SCR);
-    volatile float* xch = sink + 512 + t * 256;    // [row][half] row statistics of this tile
-    volatile float* zero = sink + 1024;
+    const uint32_t to = tmem_base + lane_addr + TM_O + 128 * t;
+    unsigned char* ost = smem_gen + OFF_OST + t * 2 * P_TILE_BYTES;
+    volatile float* scratch = reinterpret_cast<volatile float*>(smem_gen + OFF_SCR);
     // softmax in the exp2 domain: p = 2^(s*c - m), c = log2(e)/sqrt(d_head)  (transformer.py:362)
     const float c = 1.4426950408889634f * 0.08838834764831845f;
     int g = 0, n_item = 0;                         // softmax steps done so far by this warpgroup
-    // The two query tiles take turns on the SFU: exp2 throughput (16/clk/SM) is the scarce resource of
+    // The two warpgroups take turns on the SFU: exp2 throughput (16/clk/SM) is the scarce resource of
     // this kernel, so their exponential phases are serialised with a token and everything else
-    // (TMEM traffic, row max, barrier traffic) of one tile overlaps the exponentials of the other.
-    if (t == 1) nbar_arrive(NB_TOKEN0, 512);       // tile 0 goes first
-    const bool leader = (threadIdx.x & 127) == 0;  // first thread of this warpgroup
+    // (TMEM traffic, row max, barrier traffic) of one overlaps the exponentials of the other.
+    if (t == 1) nbar_arrive(NB_TOKEN0, 256);       // warpgroup 0 goes first
 
-#define TS(k) do { if (TRACE && ch == 0 && leader) TR(512 + j * 32 + t * 16 + (k)); } while (0)
+#define TS(k) do { if (TRACE && (threadIdx.x & 127) == 0) TR(512 + j * 32 + t * 16 + (k)); } while (0)
     for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n_item) {
-      const Item it = get_item(idx, npairs, T, lengths);
+      const Item it = get_item(idx, n_full, npairs, T, lengths);
       const int nkv = it.nkv, len = it.len;
+      if (!it.valid) continue;
       if (nkv == 0) {
         // every key masked: softmax of all -inf -> NaN rows, as the reference produces
         const int qrow = it.q0 + t * BM + row;
-        bf16* orow = O + ((long)it.b * T + qrow) * D + 64 * ch;
+        bf16* orow = O + ((long)it.b * T + qrow) * D;
         if (qrow < T)
-          for (int cgi = 0; cgi < 8; ++cgi)
+          for (int cgi = 0; cgi < D / 8; ++cgi)
             *reinterpret_cast<uint4*>(orow + cgi * 8) = make_uint4(0x7FC07FC0u, 0x7FC07FC0u, 0x7FC07FC0u, 0x7FC07FC0u);
         continue;
       }
       if (t >= it.ntile) continue;
       const bool pingpong = it.ntile == 2;
       float m_ref = -CUDART_INF_F;     // reference max (log2 domain) the stored P/O are relative to
-      float l_sum = 0.f;               // this thread's half of the row sum
+      float l_sum = 0.f;
 
       bool s_ready = false;          // result of the poll issued one step ahead (hides the probe latency)
       for (int j = 0; j < nkv; ++j, ++g) {
@@ -308,74 +312,71 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         tc_fence_after();
         TS(1);
         const uint32_t tsb = ts + (g & 1) * 64;
-        uint32_t sv[32];
-        tmem_ld32(tsb + 32 * ch, sv);
+        uint32_t sv[2][32];
+        tmem_ld32(tsb, sv[0]);
+        tmem_ld32(tsb + 32, sv[1]);
         // non-blocking probes, consumed later: "P V of the previous step retired", "next S ready"
         const bool o_ready = (j == 0) || mbar_test_wait(BAR(B_OFULL + t), (g - 1) & 1);
         s_ready = (j + 1 < nkv) && mbar_test_wait(BAR(B_SFULL + 2 * t + ((g + 1) & 1)), ((g + 1) >> 1) & 1);
         tmem_ld_wait();
         TS(2);
-        const int kbase = j * BKV + 32 * ch;
-        if (kbase + 32 > len) {                      // warp-uniform: only the last tile holds masked keys
+        const int kbase = j * BKV;
+        if (kbase + BKV > len) {                     // warp-uniform: only the last tile holds masked keys
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kbase + i >= len) sv[i] = 0xFF800000u;   // -inf
+          for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (kbase + h2 * 32 + i >= len) sv[h2][i] = 0xFF800000u;   // -inf
         }
-        auto half_max = [&]() {                      // 4 independent chains over this thread's 32 columns
+        auto row_max = [&]() {                       // 4 independent chains (one thread owns the row)
           float mx4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
 #pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
+          for (int i = 0; i < 32; i += 2) {
+            mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(sv[0][i]), __uint_as_float(sv[0][i + 1])));
+            mx4[((i >> 1) + 2) & 3] = fmaxf(mx4[((i >> 1) + 2) & 3], fmaxf(__uint_as_float(sv[1][i]), __uint_as_float(sv[1][i + 1])));
+          }
           return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * c;
         };
-        // full-row statistic from the two half-row threads (different warpgroups) through shared memory
-        auto row_exchange = [&](float mine, bool is_max) {
-          xch[row * 2 + ch] = mine;
-          nbar_sync(NB_PAIR + t, 256);
-          const float other = xch[row * 2 + (ch ^ 1)];
-          nbar_sync(NB_PAIR + t, 256);               // slot reusable
-          return is_max ? fmaxf(mine, other) : mine + other;
-        };
-        uint32_t pk[16];
+        uint32_t pk[32];
         float psum, p_last;
         auto exps = [&](float m_use, bool pinned) {
           float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float a0 = fmaf(__uint_as_float(sv[i]), c, -m_use);
-            const float a1 = fmaf(__uint_as_float(sv[i + 1]), c, -m_use);
+          for (int i = 0; i < 64; i += 2) {
+            const float a0 = fmaf(__uint_as_float(sv[i >> 5][i & 31]), c, -m_use);
+            const float a1 = fmaf(__uint_as_float(sv[(i + 1) >> 5][(i + 1) & 31]), c, -m_use);
             const float p0 = pinned ? fast_exp2_pinned(a0) : fast_exp2(a0);
             const float p1 = pinned ? fast_exp2_pinned(a1) : fast_exp2(a1);
             ps4[(i >> 1) & 3] += p0 + p1;
             pk[i >> 1] = pack_bf16(p0, p1);
-            if (i == 30) p_last = p1;
+            if (i == 62) p_last = p1;
           }
           psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
         };
         // The exponentials of step j > 0 start from the PREVIOUS reference max (no wait for this
         // tile's row max, which is computed alongside on otherwise idle issue slots); only if the max
         // grew by more than 2^8 is the step redone against the new reference (rare).
-        if (j == 0) m_ref = row_exchange(half_max(), true);
+        if (j == 0) m_ref = row_max();
         TS(3);
         float m_use = m_ref;
         if (pingpong) {
-          nbar_sync(t == 0 ? NB_TOKEN0 : NB_TOKEN1, 512);
+          nbar_sync(t == 0 ? NB_TOKEN0 : NB_TOKEN1, 256);
           // data dependence on a load issued after the barrier: keeps ptxas from hoisting the
           // exponentials above the token wait
-          m_use += *zero;
+          m_use += scratch[256];
         }
         exps(m_use, true);
+        const float mxl = (j == 0) ? m_ref : row_max();
         if (pingpong) {
           // ... and the token is handed over once the last exponential has been through the SFU (the
           // sums / packing / row max that follow need no SFU and may trail behind the hand-over)
-          sink[threadIdx.x] = p_last;
-          nbar_arrive(t == 0 ? NB_TOKEN1 : NB_TOKEN0, 512);
+          scratch[threadIdx.x] = p_last;
+          nbar_arrive(t == 0 ? NB_TOKEN1 : NB_TOKEN0, 256);
         }
-        const float mxl = (j == 0) ? m_ref : row_exchange(half_max(), true);
         TS(4);
         float alpha = 1.f;
         const bool rescale = (j > 0) && __any_sync(0xffffffffu, mxl > m_ref + RESCALE_THRESHOLD);
-        if (rescale) {                               // warp-uniform; identical in both half-row warps
+        if (rescale) {                               // warp-uniform, rare
           const float m_new = fmaxf(m_ref, mxl);
           alpha = fast_exp2(m_ref - m_new);
           m_ref = m_new;
@@ -387,7 +388,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           if (!o_ready) mbar_wait(BAR(B_OFULL + t), (g - 1) & 1, 10);
           tc_fence_after();
 #pragma unroll 1
-          for (int cb = 0; cb < 2; ++cb) {           // this thread's 64 O columns
+          for (int cb = 0; cb < 4; ++cb) {
             uint32_t ov[32];
             tmem_ld32(to + cb * 32, ov);
             tmem_ld_wait();
@@ -397,9 +398,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           }
         }
         TS(5);
-        // P_t (bf16 pairs) over the head of S_t[buf]; both half-row threads have loaded their scores
-        // (the row_exchange barrier above sits between those loads and this store)
-        tmem_st16(tsb + 16 * ch, pk);
+        tmem_st32(tsb, pk);                          // P_t (bf16 pairs) over the head of S_t[buf]
         // An mbarrier may run at most one phase ahead of its waiter: do not signal P_t(j) before the
         // MMA warp has consumed P_t(j-1) (it has once P V(j-1) retired).  The probe was issued at the
         // top of the step, so this is normally free.
@@ -412,55 +411,51 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         TS(7);
       }
 
-      // epilogue: O_t / l -> bf16 -> 128B-swizzled staging tile (this warpgroup's 64 columns) -> TMA store
-      // in full lines; rows past T are clipped by the tensor map.  The next item's first P V (which
+      // epilogue: O_t / l -> bf16 -> two 128B-swizzled staging tiles (64 columns each) -> TMA stores in
+      // full lines; rows past T are clipped by the tensor map.  The next item's first P V (which
       // overwrites O_t) is ordered behind these TMEM reads by this warp's own next p_full arrival.
-      if (TRACE && ch == 0 && leader) TR(32 + t * 4 + 0);
+      if (TRACE && (threadIdx.x & 127) == 0) TR(32 + t * 4 + 0);
       mbar_wait(BAR(B_OFULL + t), (g - 1) & 1, 11);
       tc_fence_after();
-      if (TRACE && ch == 0 && leader) TR(32 + t * 4 + 1);
-      float l_tot;
-      {
-        xch[row * 2 + ch] = l_sum;
-        nbar_sync(NB_PAIR + t, 256);
-        l_tot = l_sum + xch[row * 2 + (ch ^ 1)];
-        nbar_sync(NB_PAIR + t, 256);
-      }
-      const float inv = 1.0f / l_tot;
-      // the staging tile was handed to the TMA engine one whole item ago: formal guarantee only
-      if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      nbar_sync(NB_WG + wg, 128);
-      {
+      if (TRACE && (threadIdx.x & 127) == 0) TR(32 + t * 4 + 1);
+      const float inv = 1.0f / l_sum;
+      // the staging tiles were handed to the TMA engine one whole item ago: formal guarantee only
+      if ((threadIdx.x & 127) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      nbar_sync(NB_WG + t, 128);
+#pragma unroll 1
+      for (int hf = 0; hf < 2; ++hf) {
         uint32_t ov[2][32];
-        tmem_ld32(to, ov[0]);
-        tmem_ld32(to + 32, ov[1]);
+        tmem_ld32(to + hf * 64, ov[0]);
+        tmem_ld32(to + hf * 64 + 32, ov[1]);
         tmem_ld_wait();
 #pragma unroll
-        for (int q8 = 0; q8 < 8; ++q8) {
+        for (int ch = 0; ch < 8; ++ch) {
           uint4 o4;
-          const uint32_t* src = &ov[q8 >> 2][(q8 & 3) * 8];
+          const uint32_t* src = &ov[ch >> 2][(ch & 3) * 8];
           o4.x = pack_bf16(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
           o4.y = pack_bf16(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
           o4.z = pack_bf16(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
           o4.w = pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
-          *reinterpret_cast<uint4*>(ost + sw128_offset(row, q8)) = o4;
+          *reinterpret_cast<uint4*>(ost + hf * P_TILE_BYTES + sw128_offset(row, ch)) = o4;
         }
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      nbar_sync(NB_WG + wg, 128);
-      if (leader) {
-        tma_store_3d(&tm_o, ost_u32, 64 * ch, it.q0 + t * BM, it.b);
+      nbar_sync(NB_WG + t, 128);
+      if ((threadIdx.x & 127) == 0) {
+        const uint32_t src = smem_base + OFF_OST + t * 2 * P_TILE_BYTES;
+        tma_store_3d(&tm_o, src, 0, it.q0 + t * BM, it.b);
+        tma_store_3d(&tm_o, src + P_TILE_BYTES, 64, it.q0 + t * BM, it.b);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      if (TRACE && ch == 0 && leader) TR(32 + t * 4 + 2);
+      if (TRACE && (threadIdx.x & 127) == 0) TR(32 + t * 4 + 2);
     }
   }
 
-  if (warp < NSOFT_WARPS && (threadIdx.x & 127) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (warp < 8 && (threadIdx.x & 127) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
   __syncthreads();
-  if (warp == NSOFT_WARPS + 1) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -516,8 +511,13 @@ cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o,
   const int npairs = (T + 2 * BM - 1) / (2 * BM);
   const long n_items_l = (long)B * npairs;
   if (n_items_l > 0x7fffffffL) return cudaErrorInvalidValue;
-  const int n_items = (int)n_items_l;
-  const long grid = n_items < num_sms ? n_items : num_sms;
+  const int n_pairs = (int)n_items_l;
+  const long grid = n_pairs < num_sms ? n_pairs : num_sms;
+  int n_full = n_pairs, n_items = n_pairs;
+  {
+    const int rem = n_pairs % (int)grid;        // pairs in the last, partially filled round
+    if (n_pairs > grid && rem > 0 && 2 * rem <= grid) { n_full = n_pairs - rem; n_items = n_full + 2 * rem; }
+  }
   static const bool want_trace = getenv("VADB_ATTN_TRACE") != nullptr;
   if (want_trace) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -527,7 +527,7 @@ cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o,
     const int NTR = 2048;
     cudaMalloc(&dtrace, NTR * sizeof(long long));
     cudaMemsetAsync(dtrace, 0, NTR * sizeof(long long), s);
-    attn_tc_kernel<true><<<(unsigned)grid, NTHREADS, SMEM_ALLOC, s>>>(tq, tk, tv, to, o, lengths, T, npairs, n_items, dtrace);
+    attn_tc_kernel<true><<<(unsigned)grid, NTHREADS, SMEM_ALLOC, s>>>(tq, tk, tv, to, o, lengths, T, npairs, n_items, n_full, dtrace);
     std::vector<long long> ht(NTR);
     cudaMemcpyAsync(ht.data(), dtrace, NTR * sizeof(long long), cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
@@ -555,7 +555,7 @@ cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o,
   cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)SMEM_ALLOC);
   if (e != cudaSuccess) return e;
-  attn_tc_kernel<false><<<(unsigned)grid, NTHREADS, SMEM_ALLOC, s>>>(tq, tk, tv, to, o, lengths, T, npairs, n_items, nullptr);
+  attn_tc_kernel<false><<<(unsigned)grid, NTHREADS, SMEM_ALLOC, s>>>(tq, tk, tv, to, o, lengths, T, npairs, n_items, n_full, nullptr);
   return cudaGetLastError();
 }
 
