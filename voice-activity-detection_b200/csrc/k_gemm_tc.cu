@@ -19,6 +19,10 @@
 //               swizzled staging slab -> per-warp TMA store (full-line writes, no cross-warp barrier)
 // Accumulators: four 128-column TMEM slots used as a ring over (tile, n-block) jobs, so the MMAs of
 // the next job overlap the epilogue of the previous one.
+#include <stdlib.h>
+
+#include <vector>
+
 #include "tc_common.cuh"
 #include "vadb_common.cuh"
 
@@ -54,6 +58,12 @@ struct GemmTcParams {
   int res_mod;              // > 0: residual row = output row % res_mod (positional-encoding table)
   int out_f32;              // 1: fp32 output [M, N]; 0: bf16
   int out_split;            // bf16 outputs: columns [j*128, j*128+128) -> out map j when split (q,k,v)
+  // fp32 output with N == 128 only: additionally emit LayerNorm(out_row) in bf16 through tm_o1 -- the A
+  // operand of the NEXT kernel (pre-LN of the following sublayer, transformer.py:235-236), so that kernel
+  // is fed by TMA instead of register-staged producer warps
+  const float* emit_g;
+  const float* emit_b;
+  void* out_ptr[3];         // raw output pointers (epilogue stores are coalesced st.global from a staged slab)
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
@@ -73,10 +83,17 @@ __device__ __forceinline__ long window_src_row(long m, int W, int half, int jump
   return half + i + rel;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+// TRACE: developer instrumentation (VADB_GEMM_TRACE=1): CTA 0 stamps clock64() per role for its first tiles
+#define GTR(slot) do { if (TRACE && blockIdx.x == 0 && trace && (slot) < 1024) trace[(slot)] = clock64(); } while (0)
+
+// PROD = false: A arrives by TMA and the four producer warps do not exist (10 warps -> up to 168
+// registers per thread, no spills: with 224 KB of the SM given to shared memory the L1 that would absorb
+// spills is only a few KB); PROD = true: 14 warps, 128 registers.
+template <bool TRACE, bool PROD>
+__global__ void __launch_bounds__(PROD ? NTHREADS : NTHREADS - 128, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_a,
                const __grid_constant__ CUtensorMap tm_o0, const __grid_constant__ CUtensorMap tm_o1,
-               const __grid_constant__ CUtensorMap tm_o2, const GemmTcParams p) {
+               const __grid_constant__ CUtensorMap tm_o2, const GemmTcParams p, long long* trace) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -89,10 +106,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   const uint32_t bar0 = smem_base + off_bar;
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + off_bar + 8 * BAR_COUNT);
+  volatile float* xs = reinterpret_cast<volatile float*>(smem_gen + off_bar + 256);   // [2][128 rows][2] LN exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.M + 127) >> 7;
   const int NA = p.n_a_stages;
+  constexpr int EPI0 = PROD ? 6 : 2;                // first epilogue warp
 
   if (threadIdx.x == 0) {
     mbar_init(BAR(BAR_WFULL), 1);
@@ -148,11 +167,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ac0 += KC) {
       for (int nb = 0; nb < NB; ++nb, ++job) {
         const int slot = job & 3;
+        GTR(100 + job * 4 + 0);
         mbar_wait(BAR(BAR_ACCEMPTY + slot), ((job >> 2) & 1) ^ 1, 13);
+        GTR(100 + job * 4 + 1);
         for (int kc = 0; kc < KC; ++kc) {
           const int ac = ac0 + kc, s = ac % NA;
           if (nb == 0) mbar_wait(BAR(BAR_AFULL + s), (ac / NA) & 1, 14);
           tc_fence_after();
+          GTR(100 + job * 4 + 2);
           if (elect_one()) {
             const uint32_t a_lo = a_lo0 + (uint32_t)s * (BLK_BYTES >> 4);
             const uint32_t w_lo = w_lo0 + (uint32_t)(nb * KC + kc) * (BLK_BYTES >> 4);
@@ -167,10 +189,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
             if (kc == KC - 1) umma_commit(BAR(BAR_ACCFULL + slot));
           }
           __syncwarp();
+          GTR(100 + job * 4 + 3);
         }
       }
     }
-  } else if (warp < 6) {
+  } else if (PROD && warp < 6) {
     // ======================= A producers: fp32/bf16 rows -> (LayerNorm) -> bf16 UMMA operand ===========
     if (p.prod) {
       const int pw = warp - 2;
@@ -206,9 +229,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
 #pragma unroll
         for (int u = 0; u < 8; ++u) xn[u] = (blockIdx.x < n_tiles) ? load_row(row0 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      const long row_bytes = (long)cols * (src_bf16 ? 2 : 4);
+      auto prefetch_tile = [&](long tl) {            // this warp's 32 contiguous rows of tile tl -> L2
+        const long r0 = tl * 128 + pw * 32;
+        if (lane == 0 && r0 < p.M && p.win_W == 0) {
+          const long nrows = (p.M - r0 < 32) ? (p.M - r0) : 32;
+          const long bytes = (nrows * row_bytes) & ~15L;
+          if (bytes > 0) l2_prefetch(reinterpret_cast<const char*>(p.a_src) + r0 * row_bytes, (uint32_t)bytes);
+        }
+      };
+      prefetch_tile((long)blockIdx.x + gridDim.x);
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
         const int s = n % NA;
+        prefetch_tile((long)tile + 2 * gridDim.x);     // two tiles ahead of the register-staged loads
+        if (warp == 2 && lane == 0) GTR(10 + n * 4 + 0);
         mbar_wait(BAR(BAR_AEMPTY + s), ((n / NA) & 1) ^ 1, 15);
+        if (warp == 2 && lane == 0) GTR(10 + n * 4 + 1);
         unsigned char* a_half = smem_gen + off_a + s * BLK_BYTES + (lane >> 4) * HALF_BYTES;
 #pragma unroll 1
         for (int r0 = 0; r0 < 32; r0 += 8) {
@@ -221,37 +257,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
 #pragma unroll
             for (int u = 0; u < 8; ++u) xn[u] = any ? load_row(nrow0 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+          // row statistics for the 8 rows of the batch with the reduction STEPS outermost: 8 independent
+          // shuffle chains per step instead of 8 serialised 10-step chains (was ~340 cycles per row)
+          float y[8][4];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            float y0 = x[u].x, y1 = x[u].y, y2 = x[u].z, y3 = x[u].w;
+            y[u][0] = x[u].x; y[u][1] = x[u].y; y[u][2] = x[u].z; y[u][3] = x[u].w;
             if (src_bf16) {
               const uint32_t r0b = __float_as_uint(x[u].x), r1b = __float_as_uint(x[u].y);
-              y0 = __uint_as_float(r0b << 16); y1 = __uint_as_float(r0b & 0xFFFF0000u);
-              y2 = __uint_as_float(r1b << 16); y3 = __uint_as_float(r1b & 0xFFFF0000u);
+              y[u][0] = __uint_as_float(r0b << 16); y[u][1] = __uint_as_float(r0b & 0xFFFF0000u);
+              y[u][2] = __uint_as_float(r1b << 16); y[u][3] = __uint_as_float(r1b & 0xFFFF0000u);
             }
-            if (p.prod == 1) {
-              float sum = (y0 + y1) + (y2 + y3);
+          }
+          if (p.prod == 1) {
+            float st[8];
 #pragma unroll
-              for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-              const float mean = sum * (1.0f / 128.0f);
-              const float dx = y0 - mean, dy = y1 - mean, dz = y2 - mean, dw = y3 - mean;
-              float sq = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+            for (int u = 0; u < 8; ++u) st[u] = (y[u][0] + y[u][1]) + (y[u][2] + y[u][3]);
 #pragma unroll
-              for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-              const float rstd = rsqrtf(sq * (1.0f / 128.0f) + LN_EPS);
-              y0 = dx * rstd * gam.x + bet.x; y1 = dy * rstd * gam.y + bet.y;
-              y2 = dz * rstd * gam.z + bet.z; y3 = dw * rstd * gam.w + bet.w;
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+              for (int u = 0; u < 8; ++u) st[u] += __shfl_xor_sync(0xffffffffu, st[u], o);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float mean = st[u] * (1.0f / 128.0f);
+              y[u][0] -= mean; y[u][1] -= mean; y[u][2] -= mean; y[u][3] -= mean;
+              st[u] = (y[u][0] * y[u][0] + y[u][1] * y[u][1]) + (y[u][2] * y[u][2] + y[u][3] * y[u][3]);
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+              for (int u = 0; u < 8; ++u) st[u] += __shfl_xor_sync(0xffffffffu, st[u], o);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float rstd = rsqrtf(st[u] * (1.0f / 128.0f) + LN_EPS);
+              y[u][0] = y[u][0] * rstd * gam.x + bet.x; y[u][1] = y[u][1] * rstd * gam.y + bet.y;
+              y[u][2] = y[u][2] * rstd * gam.z + bet.z; y[u][3] = y[u][3] * rstd * gam.w + bet.w;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
             const int r = pw * 32 + r0 + u;
             uint2 pk;
-            pk.x = pack_bf16(y0, y1);
-            pk.y = pack_bf16(y2, y3);
+            pk.x = pack_bf16(y[u][0], y[u][1]);
+            pk.y = pack_bf16(y[u][2], y[u][3]);
             *reinterpret_cast<uint2*>(a_half + sw128_offset(r, chunk) + sub) = pk;
           }
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(BAR_AFULL + s));
+        if (warp == 2 && lane == 0) GTR(10 + n * 4 + 2);
       }
     }
   } else {
@@ -260,46 +315,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     // accumulator slot; it stages its 32-row slab in its own 4 KB buffer and issues its own TMA store,
     // so the epilogue needs no cross-warp barrier.
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
-    const int hsel = (warp - 6) >> 2;                // which column half of the slot
+    const int hsel = (warp - EPI0) >> 2;             // which column half of the slot
     const int row = q * 32 + lane;                   // row inside the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const uint32_t stg_off0 = off_stg + (uint32_t)(warp - 6) * p.n_stg * STG_BYTES;
+    const uint32_t stg_off0 = off_stg + (uint32_t)(warp - EPI0) * p.n_stg * STG_BYTES;
     int job = 0, unit = 0;
     const bool dbl = p.n_stg == 2;
     // with two slabs a store may still be reading the other one: wait only for the store before last
-    auto wait_slab_free = [&]() {
+    auto next_slab = [&]() -> uint32_t {
+      const uint32_t so = stg_off0 + (dbl ? (unit & 1) * STG_BYTES : 0);
       if (lane == 0) {
         if (dbl) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         else tma_store_wait_read0();
       }
       __syncwarp();
+      ++unit;
+      return so;
+    };
+    auto issue_store = [&](const CUtensorMap* m, uint32_t so, int c0, int r0) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(m, smem_base + so, c0, r0);
+        tma_store_commit();
+      }
     };
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long grow = (long)tile * 128 + row;
       const bool row_ok = grow < p.M;
       const float* res_row = nullptr;
       if (p.residual) res_row = p.residual + (p.res_mod > 0 ? (grow % p.res_mod) : grow) * 128 + hsel * 64;
-      // residual prefetch for the first 32-column chunk (independent of the accumulator)
-      float4 rcur[8], rnext[8];
-      if (p.residual) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          rnext[i] = row_ok ? reinterpret_cast<const float4*>(res_row)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
       for (int nb = 0; nb < NB; ++nb, ++job) {
         const int slot = job & 3;
+        if (warp == EPI0 && lane == 0) GTR(400 + job * 4 + 0);
         mbar_wait(BAR(BAR_ACCFULL + slot), (job >> 2) & 1, 16);
         tc_fence_after();
+        if (warp == EPI0 && lane == 0) GTR(400 + job * 4 + 1);
         const uint32_t tacc = tmem_base + lane_addr + slot * 128 + hsel * 64;
-        const CUtensorMap* om = (p.out_split && nb == 1) ? &tm_o1 : (p.out_split && nb == 2) ? &tm_o2 : &tm_o0;
         const int ocol0 = (p.out_split ? 0 : nb * 128) + hsel * 64;
         uint32_t v[2][32];
+        uint32_t bf_so = 0;
         tmem_ld32(tacc, v[0]);
         tmem_ld32(tacc + 32, v[1]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(BAR_ACCEMPTY + slot));   // this warp's share of the slot is drained
+        if (warp == EPI0 && lane == 0) GTR(400 + job * 4 + 2);
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
           float f[32];
@@ -316,63 +378,86 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
           }
-          if (p.residual) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
-            if (cb == 0) {                                     // prefetch the second chunk of this row
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                rnext[i] = row_ok ? reinterpret_cast<const float4*>(res_row + 32)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+          if (p.residual && row_ok) {                          // L2-hot rows (read or written a kernel ago)
+            const float4* rp = reinterpret_cast<const float4*>(res_row + cb * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              f[4 * i] += rcur[i].x; f[4 * i + 1] += rcur[i].y; f[4 * i + 2] += rcur[i].z; f[4 * i + 3] += rcur[i].w;
+              const float4 r4 = rp[i];   // plain load: the buffer may also be this kernel's output
+              f[4 * i] += r4.x; f[4 * i + 1] += r4.y; f[4 * i + 2] += r4.z; f[4 * i + 3] += r4.w;
             }
           }
           if (p.out_f32) {
             // one store unit = 32 fp32 columns (128 B per row)
-            const uint32_t so = stg_off0 + (dbl ? (unit & 1) * STG_BYTES : 0);
-            unsigned char* stg = smem_gen + so;
-            const uint32_t stg_u32 = smem_base + so;
-            wait_slab_free();
+            const uint32_t so = next_slab();
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-              *reinterpret_cast<float4*>(stg + sw128_offset(lane, c)) =
+              *reinterpret_cast<float4*>(smem_gen + so + sw128_offset(lane, c)) =
                   make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(om, stg_u32, ocol0 + cb * 32, tile * 128 + q * 32);
-              tma_store_commit();
+            issue_store(&tm_o0, so, ocol0 + cb * 32, tile * 128 + q * 32);
+            if (p.emit_g) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[cb][i] = __float_as_uint(f[i]);   // keep the row for the LayerNorm below
             }
-            ++unit;
           } else {
             // one store unit = 64 bf16 columns (128 B per row) = both 32-column chunks
-            const uint32_t so = stg_off0 + (dbl ? (unit & 1) * STG_BYTES : 0);
-            unsigned char* stg = smem_gen + so;
-            const uint32_t stg_u32 = smem_base + so;
-            if (cb == 0) wait_slab_free();
+            if (cb == 0) bf_so = next_slab();
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-              *reinterpret_cast<uint4*>(stg + sw128_offset(lane, cb * 4 + c)) =
+              *reinterpret_cast<uint4*>(smem_gen + bf_so + sw128_offset(lane, cb * 4 + c)) =
                   make_uint4(pack_bf16(f[8 * c], f[8 * c + 1]), pack_bf16(f[8 * c + 2], f[8 * c + 3]),
                              pack_bf16(f[8 * c + 4], f[8 * c + 5]), pack_bf16(f[8 * c + 6], f[8 * c + 7]));
             if (cb == 1) {
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_2d(om, stg_u32, ocol0, tile * 128 + q * 32);
-                tma_store_commit();
-              }
-              ++unit;
+              const CUtensorMap* om = (p.out_split && nb == 1) ? &tm_o1 : (p.out_split && nb == 2) ? &tm_o2 : &tm_o0;
+              issue_store(om, bf_so, ocol0, tile * 128 + q * 32);
             }
           }
         }
+        if (p.emit_g) {
+          // LayerNorm of the finished row (biased variance, eps 1e-5): this thread holds 64 of the 128
+          // columns, its partner (same lane, the other warp of this lane quarter) the rest
+          float s1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) s1 += __uint_as_float(v[i >> 5][i & 31]);
+          xs[row * 2 + hsel] = s1;
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+          const float mean = (s1 + xs[row * 2 + (hsel ^ 1)]) * (1.0f / 128.0f);
+          float s2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const float d = __uint_as_float(v[i >> 5][i & 31]) - mean;
+            s2 = fmaf(d, d, s2);
+          }
+          xs[256 + row * 2 + hsel] = s2;
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+          const float rstd = rsqrtf((s2 + xs[256 + row * 2 + (hsel ^ 1)]) * (1.0f / 128.0f) + LN_EPS);
+          const float4* gp = reinterpret_cast<const float4*>(p.emit_g + hsel * 64);
+          const float4* bp2 = reinterpret_cast<const float4*>(p.emit_b + hsel * 64);
+          const uint32_t so = next_slab();
+          unsigned char* stg = smem_gen + so;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i0 = c * 8 + e * 4;
+              const float4 g4 = __ldg(gp + (i0 >> 2)), b4 = __ldg(bp2 + (i0 >> 2));
+              const float y0 = (__uint_as_float(v[i0 >> 5][i0 & 31]) - mean) * rstd * g4.x + b4.x;
+              const float y1 = (__uint_as_float(v[(i0 + 1) >> 5][(i0 + 1) & 31]) - mean) * rstd * g4.y + b4.y;
+              const float y2 = (__uint_as_float(v[(i0 + 2) >> 5][(i0 + 2) & 31]) - mean) * rstd * g4.z + b4.z;
+              const float y3 = (__uint_as_float(v[(i0 + 3) >> 5][(i0 + 3) & 31]) - mean) * rstd * g4.w + b4.w;
+              pk[2 * e] = pack_bf16(y0, y1);
+              pk[2 * e + 1] = pack_bf16(y2, y3);
+            }
+            *reinterpret_cast<uint4*>(stg + sw128_offset(lane, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+          issue_store(&tm_o1, so, hsel * 64, tile * 128 + q * 32);
+        }
+        if (warp == EPI0 && lane == 0) GTR(400 + job * 4 + 3);
       }
     }
-    if (lane == 0) tma_store_wait_all();
   }
 
+  if (warp >= EPI0 && lane == 0) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -408,11 +493,14 @@ cudaError_t launch_gemm_tc(const GemmTcArgs& a, int num_sms, cudaStream_t s, std
   p.win_W = a.win_W; p.win_half = a.win_half; p.win_jump = a.win_jump;
   p.ln_g = a.ln_g; p.ln_b = a.ln_b;
   p.bias = a.bias; p.relu = a.relu; p.residual = a.residual; p.res_mod = a.res_mod;
-  p.out_f32 = a.out_f32; p.out_split = a.out[1] != nullptr;
+  p.out_f32 = a.out_f32; p.out_split = a.out[1] != nullptr && !a.emit_ln_g;
+  p.emit_g = a.emit_ln_g; p.emit_b = a.emit_ln_b;
+  for (int j = 0; j < 3; ++j) p.out_ptr[j] = a.out[j] ? a.out[j] : a.out[0];
+  if (a.emit_ln_g && !(a.out_f32 && a.N == 128 && a.out[1])) return bad("LayerNorm emit needs fp32 N == 128 output + out[1]");
   const uint32_t w_bytes = (uint32_t)(a.N / 128) * (a.K / 128) * BLK_BYTES;
   // shared-memory plan: resident W + A ring + per-warp staging slabs.  Prefer two staging slabs per
   // warp (a TMA store takes ~1 us to drain a slab) with at least two A stages; fall back to one slab.
-  const uint32_t LIMIT = 232448u, misc = 256 + 1024;
+  const uint32_t LIMIT = 232448u, misc = 256 + 2048 + 1024;
   const uint32_t stg1 = N_EPI_WARPS * STG_BYTES;
   p.n_stg = (w_bytes + 2 * BLK_BYTES + 2 * stg1 + misc <= LIMIT) ? 2 : 1;
   p.n_a_stages = 1;
@@ -429,18 +517,56 @@ cudaError_t launch_gemm_tc(const GemmTcArgs& a, int num_sms, cudaStream_t s, std
   const int ocols = p.out_split ? 128 : a.N;
   for (int j = 0; j < 3 && r == CUDA_SUCCESS; ++j) {
     void* optr = a.out[j] ? a.out[j] : a.out[0];
-    r = a.out_f32 ? make_tmap_2d(&to[j], optr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, ocols, 32, 32)
-                  : make_tmap_2d(&to[j], optr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, ocols, 64, 32);
+    if (a.emit_ln_g && j == 1)       // bf16 LayerNorm copy [M,128]
+      r = make_tmap_2d(&to[j], optr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, 128, 64, 32);
+    else
+      r = a.out_f32 ? make_tmap_2d(&to[j], optr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, ocols, 32, 32)
+                    : make_tmap_2d(&to[j], optr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, ocols, 64, 32);
   }
   if (r != CUDA_SUCCESS) {
     if (err) *err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")";
     return cudaErrorInvalidValue;
   }
-  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   const int n_tiles = (a.M + 127) / 128;
   const int grid = n_tiles < num_sms ? n_tiles : num_sms;
-  gemm_tc_kernel<<<grid, NTHREADS, smem, s>>>(tw, ta, to[0], to[1], to[2], p);
+  static const char* want_trace = getenv("VADB_GEMM_TRACE");     // e.g. "384" = trace launches with N == 384
+  if (want_trace && atoi(want_trace) == a.N + (p.prod ? 0 : 1000)) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (!p.prod) return bad("trace build covers the producer variant only");
+    long long* dtr = nullptr;
+    cudaMalloc(&dtr, 1024 * sizeof(long long));
+    cudaMemsetAsync(dtr, 0, 1024 * sizeof(long long), s);
+    gemm_tc_kernel<true, true><<<grid, NTHREADS, smem, s>>>(tw, ta, to[0], to[1], to[2], p, dtr);
+    std::vector<long long> ht(1024);
+    cudaMemcpyAsync(ht.data(), dtr, 1024 * sizeof(long long), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    cudaFree(dtr);
+    long long t0 = 0;
+    for (long long v : ht) if (v && (!t0 || v < t0)) t0 = v;
+    auto rel = [&](int i) { return ht[i] ? (long long)(ht[i] - t0) : -1LL; };
+    const int NBt = a.N / 128;
+    fprintf(stderr, "[gemm trace] N=%d K=%d prod=%d stages A=%d stg=%d\n", a.N, a.K, p.prod, p.n_a_stages, p.n_stg);
+    for (int n = 0; n < 7; ++n) {
+      fprintf(stderr, "[gemm trace] tile#%d producer: wait_empty %lld->%lld filled %lld\n", n, rel(10 + n * 4), rel(10 + n * 4 + 1), rel(10 + n * 4 + 2));
+      for (int nb = 0; nb < NBt; ++nb) {
+        const int job = n * NBt + nb;
+        fprintf(stderr, "[gemm trace]   job %d mma: wait_acc %lld->%lld a_ready %lld issued %lld | epi: wait %lld->%lld drained %lld stored %lld\n",
+                job, rel(100 + job * 4), rel(100 + job * 4 + 1), rel(100 + job * 4 + 2), rel(100 + job * 4 + 3),
+                rel(400 + job * 4), rel(400 + job * 4 + 1), rel(400 + job * 4 + 2), rel(400 + job * 4 + 3));
+      }
+    }
+    return cudaGetLastError();
+  }
+  if (p.prod) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    gemm_tc_kernel<false, true><<<grid, NTHREADS, smem, s>>>(tw, ta, to[0], to[1], to[2], p, nullptr);
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    gemm_tc_kernel<false, false><<<grid, NTHREADS - 128, smem, s>>>(tw, ta, to[0], to[1], to[2], p, nullptr);
+  }
   return cudaGetLastError();
 }
 

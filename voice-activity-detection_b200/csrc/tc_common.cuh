@@ -100,6 +100,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       : "memory");
 }
 
+// Asynchronous prefetch of a contiguous global range into L2 (no registers, no completion tracking):
+// lets register-staged producer loops run against L2 latency instead of HBM latency.
+__device__ __forceinline__ void l2_prefetch(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 // ------------------------------------------------------------------ TMEM allocation (one full warp)
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_result_addr, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -263,6 +269,22 @@ __device__ __forceinline__ float fast_exp2_pinned(float x) {
   float y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// Write a warp's staged [32 rows x 128 B] slab (128B-swizzled, see sw128_offset) to global memory with
+// fully coalesced 16-byte stores: each instruction covers 4 rows x 128 B = 4 whole lines.  Plain stores
+// retire without a completion wait, so one slab per warp is enough.
+__device__ __forceinline__ void store_slab(const unsigned char* stg, unsigned char* dst, long row0, long M,
+                                           long pitch_bytes, int col_byte_off, int lane) {
+  __syncwarp();                                   // every lane's row is in the slab
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3), c = lane & 7;
+    const uint4 val = *reinterpret_cast<const uint4*>(stg + sw128_offset(r, c));
+    if (row0 + r < M)
+      *reinterpret_cast<uint4*>(dst + (row0 + r) * pitch_bytes + col_byte_off + c * 16) = val;
+  }
+  __syncwarp();                                   // slab reusable
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

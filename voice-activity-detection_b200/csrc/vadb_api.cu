@@ -61,12 +61,14 @@ struct vadb_handle {
   float* pe = nullptr;       // [pe_T, 128] = PE / sqrt(d)
   int pe_T = 0;
   int num_sms = 148;
+  bool aln_valid = false;    // ws_aln holds LayerNorm(h) for the next Q/K/V GEMM
 
   // workspace, sized in frames
   size_t cap_frames = 0;
   float* ws_h = nullptr;
   void* ws_q = nullptr; void* ws_k = nullptr; void* ws_v = nullptr; void* ws_o = nullptr;
   void* ws_hid = nullptr;
+  bf16* ws_aln = nullptr;    // [frames,128] bf16 LayerNorm(h) handed from kernel to kernel (bf16 mode)
   float* ws_prob = nullptr;
 
   // host-call staging
@@ -139,7 +141,7 @@ int ensure_workspace(vadb_handle* h, size_t frames) {
   size_t cap = std::max(frames, h->cap_frames + h->cap_frames / 2);
   CU_TRY(h, cudaDeviceSynchronize());
   free_dev(h->ws_h); free_dev(h->ws_q); free_dev(h->ws_k); free_dev(h->ws_v); free_dev(h->ws_o);
-  free_dev(h->ws_hid); free_dev(h->ws_prob);
+  free_dev(h->ws_hid); free_dev(h->ws_prob); free_dev(h->ws_aln);
   h->cap_frames = 0;
   const size_t act = is_bf16_mode(h) ? sizeof(bf16) : sizeof(float);
   CU_TRY(h, cudaMalloc(&h->ws_h, cap * D * sizeof(float)));
@@ -149,6 +151,7 @@ int ensure_workspace(vadb_handle* h, size_t frames) {
   CU_TRY(h, cudaMalloc(&h->ws_o, cap * D * act));
   CU_TRY(h, cudaMalloc(&h->ws_hid, cap * DFF * act));
   CU_TRY(h, cudaMalloc(&h->ws_prob, cap * sizeof(float)));
+  CU_TRY(h, cudaMalloc(&h->ws_aln, cap * D * sizeof(bf16)));
   h->cap_frames = cap;
   return VADB_OK;
 }
@@ -202,36 +205,44 @@ int run_encoder(vadb_handle* h, const int32_t* lengths, int Bc, int T, float* pr
     const LayerOffsets& lo = h->lay.layers[l];
     int rc;
     if (bf) {
-      // bf16 mode: every Linear on the tensor cores (k_gemm_tc.cu), attention in k_attn_tc.cu
-      {  // a = LN1(h); q,k,v = a W^T + b        (transformer.py:235-236, :281-284)
+      // bf16 mode: every Linear on the tensor cores (k_gemm_tc.cu / k_ffn_tc.cu), attention in k_attn_tc.cu.
+      // Each kernel that produces the residual stream h also emits LayerNorm(h) of the NEXT sublayer in
+      // bf16 (ws_aln), so every GEMM reads its A operand by TMA.  ws_aln holds LN1_l(h) on entry
+      // (front end / previous layer); it is rebuilt here when the front end took the fp32 fallback.
+      const bool have_aln = h->aln_valid;
+      {  // q,k,v = LN1(h) W^T + b                (transformer.py:235-236, :281-284)
         GemmTcArgs g = {};
         g.M = M; g.N = 3 * D; g.K = D; g.w_bf16 = h->wqkv_bf + (size_t)l * 3 * D * D;
-        g.a_f32 = h->ws_h; g.ln_g = w + lo.ln1_g; g.ln_b = w + lo.ln1_b;
+        if (have_aln) g.a_bf16 = h->ws_aln;
+        else { g.a_f32 = h->ws_h; g.ln_g = w + lo.ln1_g; g.ln_b = w + lo.ln1_b; }
         g.bias = h->bqkv + (size_t)l * 3 * D;
         g.out[0] = h->ws_q; g.out[1] = h->ws_k; g.out[2] = h->ws_v;
         if ((rc = gemm_tc(h, g, s))) return rc;
       }
       if ((rc = attention(h, h->ws_q, h->ws_k, h->ws_v, h->ws_o, VADB_BF16, lengths, Bc, T, s))) return rc;
-      {  // h += o Wo^T + bo                      (transformer.py:347, :237)
+      {  // h += o Wo^T + bo (transformer.py:347, :237); emits LN2(h) for the feed-forward sublayer
         GemmTcArgs g = {};
         g.M = M; g.N = D; g.K = D; g.w_bf16 = h->wo_bf + (size_t)l * D * D;
         g.a_bf16 = (const bf16*)h->ws_o; g.bias = w + lo.bo; g.residual = h->ws_h;
         g.out_f32 = 1; g.out[0] = h->ws_h;
+        g.out[1] = h->ws_aln; g.emit_ln_g = w + lo.ln2_g; g.emit_ln_b = w + lo.ln2_b;
         if ((rc = gemm_tc(h, g, s))) return rc;
       }
-      {  // hid = relu(LN2(h) W1^T + b1)          (transformer.py:370-372)
-        GemmTcArgs g = {};
-        g.M = M; g.N = DFF; g.K = D; g.w_bf16 = h->w1_bf + (size_t)l * DFF * D;
-        g.a_f32 = h->ws_h; g.ln_g = w + lo.ln2_g; g.ln_b = w + lo.ln2_b;
-        g.bias = w + lo.b1; g.relu = 1; g.out[0] = h->ws_hid;
-        if ((rc = gemm_tc(h, g, s))) return rc;
-      }
-      {  // h += hid W2^T + b2                    (transformer.py:374, :237)
-        GemmTcArgs g = {};
-        g.M = M; g.N = D; g.K = DFF; g.w_bf16 = h->w2_bf + (size_t)l * D * DFF;
-        g.a_bf16 = (const bf16*)h->ws_hid; g.bias = w + lo.b2; g.residual = h->ws_h;
-        g.out_f32 = 1; g.out[0] = h->ws_h;
-        if ((rc = gemm_tc(h, g, s))) return rc;
+      {  // h += relu(LN2(h) W1^T + b1) W2^T + b2 (transformer.py:234-238, :370-375), hidden kept on chip;
+         // emits LN1 of the next layer
+        FfnTcArgs f = {};
+        f.M = M; f.h = h->ws_h; f.a_ln = h->ws_aln;
+        f.w1_bf16 = h->w1_bf + (size_t)l * DFF * D; f.b1 = w + lo.b1;
+        f.w2_bf16 = h->w2_bf + (size_t)l * D * DFF; f.b2 = w + lo.b2;
+        if (l + 1 < h->cfg.num_layers) {
+          f.emit_out = h->ws_aln;
+          f.emit_ln_g = w + h->lay.layers[l + 1].ln1_g; f.emit_ln_b = w + h->lay.layers[l + 1].ln1_b;
+        }
+        std::string err;
+        cudaError_t e = launch_ffn_tc(f, h->num_sms, s, &err);
+        if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("ffn_tc: ") + cudaGetErrorString(e) + " " + err);
+        h->launches++;
+        h->aln_valid = true;
       }
       continue;
     }
@@ -287,8 +298,13 @@ int front_end(vadb_handle* h, const void* x, int x_is_bf16, int M, int pe_T, int
     g.win_W = win_W; g.win_half = win_half; g.win_jump = win_jump;
     g.bias = h->w32 + h->lay.b_in; g.residual = h->pe; g.res_mod = pe_T;
     g.out_f32 = 1; g.out[0] = h->ws_h;
+    // also emit LN1 of layer 0 in bf16: the A operand of the first Q/K/V GEMM
+    g.out[1] = h->ws_aln;
+    g.emit_ln_g = h->w32 + h->lay.layers[0].ln1_g; g.emit_ln_b = h->w32 + h->lay.layers[0].ln1_b;
+    h->aln_valid = true;
     return gemm_tc(h, g, s);
   }
+  h->aln_valid = false;
   GemmArgs g = {};
   g.A = x; g.a_is_bf16 = x_is_bf16;
   g.W = h->w32 + h->lay.w_in; g.bias = h->w32 + h->lay.b_in;
@@ -379,7 +395,7 @@ void vadb_destroy(vadb_handle* h) {
   free_dev(h->wqkv_bf); free_dev(h->wo_bf); free_dev(h->w1_bf); free_dev(h->w2_bf); free_dev(h->win_bf);
   free_dev(h->pe);
   free_dev(h->ws_h); free_dev(h->ws_q); free_dev(h->ws_k); free_dev(h->ws_v); free_dev(h->ws_o);
-  free_dev(h->ws_hid); free_dev(h->ws_prob);
+  free_dev(h->ws_hid); free_dev(h->ws_prob); free_dev(h->ws_aln);
   if (h->pin_in) cudaFreeHost(h->pin_in);
   if (h->pin_out) cudaFreeHost(h->pin_out);
   if (h->dev_in) cudaFree(h->dev_in);

@@ -82,8 +82,26 @@ struct GemmTcArgs {
   int res_mod;             // > 0: residual row = m % res_mod (positional-encoding table [T,128])
   int out_f32;             // fp32 [M,N] output, else bf16
   void* out[3];            // out[1], out[2] set -> columns split in 128-wide blocks (q, k, v)
+  // fp32 N == 128 outputs: also write LayerNorm(out_row) (gamma/beta of the NEXT sublayer) as bf16 to out[1]
+  const float* emit_ln_g;
+  const float* emit_ln_b;
 };
 cudaError_t launch_gemm_tc(const GemmTcArgs& a, int num_sms, cudaStream_t s, std::string* err);
+
+// fused LN2 + FFN1 + ReLU + FFN2 + residual (k_ffn_tc.cu); h is updated in place
+struct FfnTcArgs {
+  int M;
+  float* h;                // [M,128] fp32 residual stream (in/out)
+  const bf16* a_ln;        // [M,128] bf16 LayerNorm(h) written by the previous kernel (A operand, via TMA)
+  bf16* emit_out;          // optional: LayerNorm of the OUTPUT rows for the next layer's Q/K/V GEMM
+  const float* emit_ln_g;
+  const float* emit_ln_b;
+  const bf16* w1_bf16;     // [512,128]
+  const float* b1;         // [512]
+  const bf16* w2_bf16;     // [128,512]
+  const float* b2;         // [128]
+};
+cudaError_t launch_ffn_tc(const FfnTcArgs& a, int num_sms, cudaStream_t s, std::string* err);
 
 // final LayerNorm + classifier + sigmoid/log-softmax (k_classifier.cu)
 cudaError_t launch_classifier(const float* h, const float* g, const float* b, const float* wc,
