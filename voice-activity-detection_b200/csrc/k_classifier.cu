@@ -24,34 +24,56 @@ __global__ void __launch_bounds__(256) classifier_kernel(const float* __restrict
   const float4 w0 = __ldg(reinterpret_cast<const float4*>(wc) + lane);
   const float4 w1 = __ldg(reinterpret_cast<const float4*>(wc + D) + lane);
   const float b0 = __ldg(bc), b1 = __ldg(bc + 1);
-  for (long row = warp; row < M; row += nwarps) {
-    const float4 x = __ldg(reinterpret_cast<const float4*>(h + row * D) + lane);
-    float s = x.x + x.y + x.z + x.w;
+  // four rows per warp iteration: four independent 512-byte row loads in flight per warp
+  for (long row0 = warp * 4; row0 < M; row0 += nwarps * 4) {
+    float4 xr[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s * (1.0f / D);
-    const float dx = x.x - mean, dy = x.y - mean, dz = x.z - mean, dw = x.w - mean;
-    float q = dx * dx + dy * dy + dz * dz + dw * dw;
+    for (int u = 0; u < 4; ++u)
+      xr[u] = (row0 + u < M) ? __ldg(reinterpret_cast<const float4*>(h + (row0 + u) * D) + lane)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    float st[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = 1.0f / sqrtf(q * (1.0f / D) + LN_EPS);
-    const float y0 = dx * rstd * gam.x + bet.x, y1 = dy * rstd * gam.y + bet.y;
-    const float y2 = dz * rstd * gam.z + bet.z, y3 = dw * rstd * gam.w + bet.w;
-    float z0 = y0 * w0.x + y1 * w0.y + y2 * w0.z + y3 * w0.w;
-    float z1 = y0 * w1.x + y1 * w1.y + y2 * w1.z + y3 * w1.w;
+    for (int u = 0; u < 4; ++u) st[u] = (xr[u].x + xr[u].y) + (xr[u].z + xr[u].w);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      z0 += __shfl_xor_sync(0xffffffffu, z0, o);
-      z1 += __shfl_xor_sync(0xffffffffu, z1, o);
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) st[u] += __shfl_xor_sync(0xffffffffu, st[u], o);
+    float d[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float mean = st[u] * (1.0f / D);
+      d[u][0] = xr[u].x - mean; d[u][1] = xr[u].y - mean; d[u][2] = xr[u].z - mean; d[u][3] = xr[u].w - mean;
+      st[u] = (d[u][0] * d[u][0] + d[u][1] * d[u][1]) + (d[u][2] * d[u][2] + d[u][3] * d[u][3]);
     }
-    if (lane == 0) {
-      z0 += b0; z1 += b1;
-      // log_softmax([z0, z1]) computed stably
-      const float mx = fmaxf(z0, z1);
-      const float lse = mx + log1pf(expf(-fabsf(z1 - z0)));
-      const float lp0 = z0 - lse, lp1 = z1 - lse;
-      if (logp) { logp[row * 2] = lp0; logp[row * 2 + 1] = lp1; }
-      if (prob) prob[row] = 1.0f / (1.0f + expf(z0 - z1));   // softmax(logp)[1]
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) st[u] += __shfl_xor_sync(0xffffffffu, st[u], o);
+    float z0[4], z1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float rstd = 1.0f / sqrtf(st[u] * (1.0f / D) + LN_EPS);
+      const float y0 = d[u][0] * rstd * gam.x + bet.x, y1 = d[u][1] * rstd * gam.y + bet.y;
+      const float y2 = d[u][2] * rstd * gam.z + bet.z, y3 = d[u][3] * rstd * gam.w + bet.w;
+      z0[u] = y0 * w0.x + y1 * w0.y + y2 * w0.z + y3 * w0.w;
+      z1[u] = y0 * w1.x + y1 * w1.y + y2 * w1.z + y3 * w1.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        z0[u] += __shfl_xor_sync(0xffffffffu, z0[u], o);
+        z1[u] += __shfl_xor_sync(0xffffffffu, z1[u], o);
+      }
+    if (lane < 4 && row0 + lane < M) {
+      const long row = row0 + lane;
+      const float a0 = (lane == 0 ? z0[0] : lane == 1 ? z0[1] : lane == 2 ? z0[2] : z0[3]) + b0;
+      const float a1 = (lane == 0 ? z1[0] : lane == 1 ? z1[1] : lane == 2 ? z1[2] : z1[3]) + b1;
+      // log_softmax([a0, a1]) computed stably
+      const float mx = fmaxf(a0, a1);
+      const float lse = mx + log1pf(expf(-fabsf(a1 - a0)));
+      if (logp) { logp[row * 2] = a0 - lse; logp[row * 2 + 1] = a1 - lse; }
+      if (prob) prob[row] = 1.0f / (1.0f + expf(a0 - a1));   // softmax(logp)[1]
     }
   }
 }
@@ -62,7 +84,7 @@ cudaError_t launch_classifier(const float* h, const float* g, const float* b, co
                               const float* bc, int M, float* prob, float* logp, cudaStream_t s) {
   if (M <= 0) return cudaSuccess;
   const int warps_per_block = 8;
-  long blocks = ((long)M + warps_per_block - 1) / warps_per_block;
+  long blocks = ((long)M + 4 * warps_per_block - 1) / (4 * warps_per_block);
   if (blocks > 148 * 16) blocks = 148 * 16;
   classifier_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(h, g, b, wc, bc, M, prob, logp);
   return cudaGetLastError();

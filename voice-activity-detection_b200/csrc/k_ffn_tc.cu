@@ -361,8 +361,14 @@ cudaError_t launch_ffn_tc(const FfnTcArgs& a, int num_sms, cudaStream_t s, std::
   p.M = a.M; p.h = a.h; p.b1 = a.b1; p.b2 = a.b2;
   p.emit_g = a.emit_out ? a.emit_ln_g : nullptr; p.emit_b = a.emit_ln_b;
   p.h_out = a.h; p.emit_out = a.emit_out;
-  cudaError_t e = cudaFuncSetAttribute(ffn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
-  if (e != cudaSuccess) return e;
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(ffn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
+    if (e != cudaSuccess) return e;
+    attr_dev = dev;
+  }
   const int n_tiles = (a.M + 127) / 128;
   const int grid = n_tiles < num_sms ? n_tiles : num_sms;
   ffn_tc_kernel<<<grid, NTHREADS, SMEM_ALLOC, s>>>(t1, t2, ta, to, te, p);

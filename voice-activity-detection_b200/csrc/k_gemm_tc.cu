@@ -531,13 +531,14 @@ cudaError_t launch_gemm_tc(const GemmTcArgs& a, int num_sms, cudaStream_t s, std
   const int grid = n_tiles < num_sms ? n_tiles : num_sms;
   static const char* want_trace = getenv("VADB_GEMM_TRACE");     // e.g. "384" = trace launches with N == 384
   if (want_trace && atoi(want_trace) == a.N + (p.prod ? 0 : 1000)) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = p.prod ? cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if (!p.prod) return bad("trace build covers the producer variant only");
     long long* dtr = nullptr;
     cudaMalloc(&dtr, 1024 * sizeof(long long));
     cudaMemsetAsync(dtr, 0, 1024 * sizeof(long long), s);
-    gemm_tc_kernel<true, true><<<grid, NTHREADS, smem, s>>>(tw, ta, to[0], to[1], to[2], p, dtr);
+    if (p.prod) gemm_tc_kernel<true, true><<<grid, NTHREADS, smem, s>>>(tw, ta, to[0], to[1], to[2], p, dtr);
+    else gemm_tc_kernel<true, false><<<grid, NTHREADS - 128, smem, s>>>(tw, ta, to[0], to[1], to[2], p, dtr);
     std::vector<long long> ht(1024);
     cudaMemcpyAsync(ht.data(), dtr, 1024 * sizeof(long long), cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
@@ -558,15 +559,18 @@ cudaError_t launch_gemm_tc(const GemmTcArgs& a, int num_sms, cudaStream_t s, std
     }
     return cudaGetLastError();
   }
-  if (p.prod) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // opt in to the full dynamic shared-memory carve-out once per device and variant
+  static thread_local int attr_dev[2] = {-1, -1};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr_dev[p.prod ? 1 : 0] != dev) {
+    cudaError_t e = p.prod ? cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)
+                           : cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
-    gemm_tc_kernel<false, true><<<grid, NTHREADS, smem, s>>>(tw, ta, to[0], to[1], to[2], p, nullptr);
-  } else {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    gemm_tc_kernel<false, false><<<grid, NTHREADS - 128, smem, s>>>(tw, ta, to[0], to[1], to[2], p, nullptr);
+    attr_dev[p.prod ? 1 : 0] = dev;
   }
+  if (p.prod) gemm_tc_kernel<false, true><<<grid, NTHREADS, smem, s>>>(tw, ta, to[0], to[1], to[2], p, nullptr);
+  else gemm_tc_kernel<false, false><<<grid, NTHREADS - 128, smem, s>>>(tw, ta, to[0], to[1], to[2], p, nullptr);
   return cudaGetLastError();
 }
 

@@ -510,7 +510,9 @@ int vadb_forward_host(vadb_handle* h, const float* x, const int32_t* lengths, in
   cudaStream_t s_copy = h->own_stream, s_comp = h->own_stream2;
   const int F = h->cfg.feature_size;
   const size_t clip_in = (size_t)T * F * sizeof(float);
-  int C = (int)std::max<size_t>(1, ((size_t)8 << 20) / std::max<size_t>(clip_in, 1));   // ~8 MB chunks
+  // >= 8 MB per chunk, at most 3 chunks: enough overlap, few (small, launch-bound) forward passes
+  int C = (int)std::max<size_t>(1, ((size_t)8 << 20) / std::max<size_t>(clip_in, 1));
+  C = std::max(C, (B + 2) / 3);
   C = std::min(C, B);
   const int n_chunks = (B + C - 1) / C;
   const size_t n = (size_t)B * T;
