@@ -38,7 +38,7 @@ constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 2048;      // barriers + LayerNo
 constexpr uint32_t SMEM_ALLOC = SMEM_BYTES;                // the dynamic smem window is declared 1024-aligned
 
 enum { B_AFULL = 0, B_AEMPTY = 2, B_WFULL = 4 /* 4 slots reserved */, B_WEMPTY = 8, B_HIDFULL = 12, B_HIDBF = 14, B_OUTFULL = 16,
-       B_OUTEMPTY = 18, B_COUNT = 20 };
+       B_OUTEMPTY = 18, B_RES = 20 /* one per epilogue warp */, B_COUNT = 28 };
 
 constexpr uint32_t TM_HID = 0;      // hidden slot s at columns 128 s (fp32); its bf16 copy (A operand of GEMM3)
                                     // is written by each epilogue thread over the head of its own 64 columns
@@ -97,6 +97,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__
       mbar_init(BAR(B_OUTFULL + s), 1);
       mbar_init(BAR(B_OUTEMPTY + s), N_EPI_WARPS);
     }
+    for (int w = 0; w < N_EPI_WARPS; ++w) mbar_init(BAR(B_RES + w), 1);
     mbar_fence_init();
   }
   if (warp == 0 && lane == 0) {
@@ -192,14 +193,8 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t stg_off0 = OFF_STG + (uint32_t)(warp - 2) * 2 * STG_BYTES;      // this warp's two staging slabs
-    int n = 0, unit = 0;
-    auto next_slab = [&]() -> uint32_t {
-      const uint32_t so = stg_off0 + (unit & 1) * STG_BYTES;
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-      __syncwarp();
-      ++unit;
-      return so;
-    };
+    int n = 0;
+    const uint32_t res_bar = BAR(B_RES + (warp - 2));
     auto issue_store = [&](const CUtensorMap* m, uint32_t so, int c0, int r0) {
       fence_proxy_async_smem();
       __syncwarp();
@@ -210,9 +205,16 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__
     };
     int hid_uses[2] = {0, 0};
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-      const long grow = (long)tile * 128 + row;
-      const bool row_ok = grow < p.M;
-      const float4* res_row = reinterpret_cast<const float4*>(p.h + grow * 128 + hsel * 64);
+      // This warp's share of the residual rows ([32 rows x 64 fp32] of h) lands by TMA in its own two staging
+      // slabs while the hidden blocks are processed; the final epilogue updates the slabs in place and
+      // stores them back.  (Per-thread row loads here cost two exposed DRAM round trips per tile.)
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // last tile's stores have left the slabs
+        mbar_arrive_expect_tx(res_bar, 2 * STG_BYTES);
+        tma_load_2d(smem_base + stg_off0, &tm_out, res_bar, hsel * 64, tile * 128 + q * 32);
+        tma_load_2d(smem_base + stg_off0 + STG_BYTES, &tm_out, res_bar, hsel * 64 + 32, tile * 128 + q * 32);
+      }
+      __syncwarp();
       for (int nb = 0; nb < 4; ++nb) {
         const int hs = nb & 1;
         mbar_wait(BAR(B_HIDFULL + hs), hid_uses[hs] & 1, 27);
@@ -242,9 +244,6 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__
       }
       // final epilogue: + b2 + residual -> fp32 -> staging -> TMA store (two units of 32 columns)
       const int ob = n & 1;
-      float4 res[8];                       // residual chunk 0 (L2-hot: the producers read these rows for LN)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) res[i] = row_ok ? res_row[i] : make_float4(0.f, 0.f, 0.f, 0.f);
       mbar_wait(BAR(B_OUTFULL + ob), (n >> 1) & 1, 28);
       tc_fence_after();
       const uint32_t tacc = tmem_base + lane_addr + TM_OUT + 128u * ob + 64u * hsel;
@@ -255,26 +254,21 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_OUTEMPTY + ob));
+      mbar_wait(res_bar, n & 1, 29);
 #pragma unroll
       for (int cb = 0; cb < 2; ++cb) {
         const float4* bp = reinterpret_cast<const float4*>(p.b2 + hsel * 64 + cb * 32);
-        const uint32_t so = next_slab();
+        const uint32_t so = stg_off0 + cb * STG_BYTES;
         unsigned char* stg = smem_gen + so;
-        float4 rcur[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rcur[i] = res[i];
-        if (cb == 0) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) res[i] = row_ok ? res_row[8 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
           const float4 b4 = __ldg(bp + c4);
-          const float4 r4 = rcur[c4];
+          float4* cell = reinterpret_cast<float4*>(stg + sw128_offset(lane, c4));
+          const float4 r4 = *cell;
           const uint32_t* s4 = &v[cb][c4 * 4];
           const float4 f4 = make_float4(__uint_as_float(s4[0]) + b4.x + r4.x, __uint_as_float(s4[1]) + b4.y + r4.y,
                                         __uint_as_float(s4[2]) + b4.z + r4.z, __uint_as_float(s4[3]) + b4.w + r4.w);
-          *reinterpret_cast<float4*>(stg + sw128_offset(lane, c4)) = f4;
+          *cell = f4;
           v[cb][c4 * 4] = __float_as_uint(f4.x); v[cb][c4 * 4 + 1] = __float_as_uint(f4.y);
           v[cb][c4 * 4 + 2] = __float_as_uint(f4.z); v[cb][c4 * 4 + 3] = __float_as_uint(f4.w);
         }
@@ -300,7 +294,9 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__
         const float rstd = rsqrtf((s2 + xs[256 + row * 2 + (hsel ^ 1)]) * (1.0f / 128.0f) + LN_EPS);
         const float4* gp = reinterpret_cast<const float4*>(p.emit_g + hsel * 64);
         const float4* bp2 = reinterpret_cast<const float4*>(p.emit_b + hsel * 64);
-        const uint32_t so = next_slab();
+        const uint32_t so = stg_off0;                 // slab 0 again, once its fp32 store has been read out
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
         unsigned char* stg = smem_gen + so;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {

@@ -38,7 +38,9 @@ constexpr uint32_t HALF_BYTES = 128 * 128;        // [128 rows x 64 k] bf16
 constexpr uint32_t STG_BYTES = 32 * 128;          // per-warp staging: 32 rows x 128 B
 constexpr uint32_t IDESC = idesc_bf16(128, 128, 0, 0);
 
-enum { BAR_WFULL = 0, BAR_AFULL = 1, BAR_AEMPTY = 4, BAR_ACCFULL = 7, BAR_ACCEMPTY = 11, BAR_COUNT = 15 };
+enum { BAR_WFULL = 0, BAR_AFULL = 1, BAR_AEMPTY = 4, BAR_ACCFULL = 7, BAR_ACCEMPTY = 11, BAR_RFULL = 15, BAR_REMPTY = 16,
+       BAR_COUNT = 17 };
+constexpr uint32_t RES_BYTES = 128 * 128 * 4;     // one fp32 residual tile = four SW128 boxes of 32 columns
 
 struct GemmTcParams {
   int M, N, K;              // N multiple of 128, <= 512; K (padded) multiple of 128; N*K <= 65536
@@ -56,6 +58,8 @@ struct GemmTcParams {
   int relu;
   const float* residual;    // fp32 [*, 128] added in the epilogue (N == 128) or nullptr
   int res_mod;              // > 0: residual row = output row % res_mod (positional-encoding table)
+  int res_tma;              // residual tiles arrive by TMA (tm_o2 doubles as their load map) one tile ahead of
+                            // the epilogue instead of per-thread row loads whose DRAM latency nothing hides
   int out_f32;              // 1: fp32 output [M, N]; 0: bf16
   int out_split;            // bf16 outputs: columns [j*128, j*128+128) -> out map j when split (q,k,v)
   // fp32 output with N == 128 only: additionally emit LayerNorm(out_row) in bf16 through tm_o1 -- the A
@@ -94,14 +98,19 @@ __global__ void __launch_bounds__(PROD ? NTHREADS : NTHREADS - 128, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_a,
                const __grid_constant__ CUtensorMap tm_o0, const __grid_constant__ CUtensorMap tm_o1,
                const __grid_constant__ CUtensorMap tm_o2, const GemmTcParams p, long long* trace) {
-  extern __shared__ unsigned char smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  unsigned char* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  unsigned char* smem_gen = smem_raw;
+  if ((smem_base & 1023u) != 0) {   // 128B-swizzled tiles need 1024-byte alignment
+    if (threadIdx.x == 0) printf("vadb: gemm kernel shared memory window not 1024-byte aligned\n");
+    __trap();
+  }
 
   const int NB = p.N >> 7, KC = p.K >> 7;
   const uint32_t off_w = 0;
   const uint32_t off_a = off_w + (uint32_t)(NB * KC) * BLK_BYTES;
-  const uint32_t off_stg = off_a + (uint32_t)p.n_a_stages * BLK_BYTES;
+  const uint32_t off_r = off_a + (uint32_t)p.n_a_stages * BLK_BYTES;
+  const uint32_t off_stg = off_r + (p.res_tma ? RES_BYTES : 0u);
   const uint32_t off_bar = off_stg + (uint32_t)p.n_stg * N_EPI_WARPS * STG_BYTES;
   const uint32_t bar0 = smem_base + off_bar;
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -123,6 +132,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       mbar_init(BAR(BAR_ACCFULL + s), 1);
       mbar_init(BAR(BAR_ACCEMPTY + s), N_EPI_WARPS);
     }
+    mbar_init(BAR(BAR_RFULL), 1);
+    mbar_init(BAR(BAR_REMPTY), N_EPI_WARPS);
     mbar_fence_init();
   }
   if (warp == 0 && lane == 0) {
@@ -146,8 +157,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
             tma_load_2d(smem_base + off_w + (uint32_t)(nb * KC + kc) * BLK_BYTES + hf * HALF_BYTES, &tm_w,
                         BAR(BAR_WFULL), kc * 128 + hf * 64, nb * 128);
       if (!p.prod) {
-        int ac = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        int ac = 0, n = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
           for (int kc = 0; kc < KC; ++kc, ++ac) {
             const int s = ac % NA;
             mbar_wait(BAR(BAR_AEMPTY + s), ((ac / NA) & 1) ^ 1, 11);
@@ -156,6 +167,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
               tma_load_2d(smem_base + off_a + s * BLK_BYTES + hf * HALF_BYTES, &tm_a, BAR(BAR_AFULL + s),
                           kc * 128 + hf * 64, tile * 128);
           }
+          if (p.res_tma) {        // residual rows of this tile (rows past M read as zeros)
+            mbar_wait(BAR(BAR_REMPTY), (n & 1) ^ 1, 18);
+            mbar_arrive_expect_tx(BAR(BAR_RFULL), RES_BYTES);
+            for (int c = 0; c < 4; ++c)
+              tma_load_2d(smem_base + off_r + c * (RES_BYTES / 4), &tm_o2, BAR(BAR_RFULL), c * 32, tile * 128);
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -340,7 +358,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         tma_store_commit();
       }
     };
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const long grow = (long)tile * 128 + row;
       const bool row_ok = grow < p.M;
       const float* res_row = nullptr;
@@ -362,50 +381,72 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(BAR_ACCEMPTY + slot));   // this warp's share of the slot is drained
         if (warp == EPI0 && lane == 0) GTR(400 + job * 4 + 2);
+        // phase 1: bias / ReLU / residual, in place in the accumulator registers
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
-          float f[32];
           const float4* bp = reinterpret_cast<const float4*>(p.bias + nb * 128 + hsel * 64 + cb * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 b4 = __ldg(bp + i);                  // warp-uniform address: one transaction
-            f[4 * i] = __uint_as_float(v[cb][4 * i]) + b4.x;
-            f[4 * i + 1] = __uint_as_float(v[cb][4 * i + 1]) + b4.y;
-            f[4 * i + 2] = __uint_as_float(v[cb][4 * i + 2]) + b4.z;
-            f[4 * i + 3] = __uint_as_float(v[cb][4 * i + 3]) + b4.w;
+            v[cb][4 * i] = __float_as_uint(__uint_as_float(v[cb][4 * i]) + b4.x);
+            v[cb][4 * i + 1] = __float_as_uint(__uint_as_float(v[cb][4 * i + 1]) + b4.y);
+            v[cb][4 * i + 2] = __float_as_uint(__uint_as_float(v[cb][4 * i + 2]) + b4.z);
+            v[cb][4 * i + 3] = __float_as_uint(__uint_as_float(v[cb][4 * i + 3]) + b4.w);
           }
           if (p.relu) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+            for (int i = 0; i < 32; ++i) v[cb][i] = __float_as_uint(fmaxf(__uint_as_float(v[cb][i]), 0.f));
           }
-          if (p.residual && row_ok) {                          // L2-hot rows (read or written a kernel ago)
+          if (p.res_tma) {
+            if (cb == 0) mbar_wait(BAR(BAR_RFULL), tcount & 1, 19);
+            const unsigned char* rb = smem_gen + off_r + (uint32_t)(hsel * 2 + cb) * (RES_BYTES / 4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 r4 = *reinterpret_cast<const float4*>(rb + sw128_offset(row, i));
+              v[cb][4 * i] = __float_as_uint(__uint_as_float(v[cb][4 * i]) + r4.x);
+              v[cb][4 * i + 1] = __float_as_uint(__uint_as_float(v[cb][4 * i + 1]) + r4.y);
+              v[cb][4 * i + 2] = __float_as_uint(__uint_as_float(v[cb][4 * i + 2]) + r4.z);
+              v[cb][4 * i + 3] = __float_as_uint(__uint_as_float(v[cb][4 * i + 3]) + r4.w);
+            }
+          } else if (p.residual && row_ok) {                   // positional table / non-TMA residual rows
             const float4* rp = reinterpret_cast<const float4*>(res_row + cb * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 r4 = rp[i];   // plain load: the buffer may also be this kernel's output
-              f[4 * i] += r4.x; f[4 * i + 1] += r4.y; f[4 * i + 2] += r4.z; f[4 * i + 3] += r4.w;
+              v[cb][4 * i] = __float_as_uint(__uint_as_float(v[cb][4 * i]) + r4.x);
+              v[cb][4 * i + 1] = __float_as_uint(__uint_as_float(v[cb][4 * i + 1]) + r4.y);
+              v[cb][4 * i + 2] = __float_as_uint(__uint_as_float(v[cb][4 * i + 2]) + r4.z);
+              v[cb][4 * i + 3] = __float_as_uint(__uint_as_float(v[cb][4 * i + 3]) + r4.w);
             }
           }
+        }
+        if (p.res_tma) {          // residual tile consumed: the TMA warp may fetch the next one
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(BAR_REMPTY));
+        }
+        // phase 2: stage and store
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
           if (p.out_f32) {
             // one store unit = 32 fp32 columns (128 B per row)
             const uint32_t so = next_slab();
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-              *reinterpret_cast<float4*>(smem_gen + so + sw128_offset(lane, c)) =
-                  make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
+              *reinterpret_cast<uint4*>(smem_gen + so + sw128_offset(lane, c)) =
+                  make_uint4(v[cb][4 * c], v[cb][4 * c + 1], v[cb][4 * c + 2], v[cb][4 * c + 3]);
             issue_store(&tm_o0, so, ocol0 + cb * 32, tile * 128 + q * 32);
-            if (p.emit_g) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[cb][i] = __float_as_uint(f[i]);   // keep the row for the LayerNorm below
-            }
           } else {
             // one store unit = 64 bf16 columns (128 B per row) = both 32-column chunks
             if (cb == 0) bf_so = next_slab();
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t* f = &v[cb][8 * c];
               *reinterpret_cast<uint4*>(smem_gen + bf_so + sw128_offset(lane, cb * 4 + c)) =
-                  make_uint4(pack_bf16(f[8 * c], f[8 * c + 1]), pack_bf16(f[8 * c + 2], f[8 * c + 3]),
-                             pack_bf16(f[8 * c + 4], f[8 * c + 5]), pack_bf16(f[8 * c + 6], f[8 * c + 7]));
+                  make_uint4(pack_bf16(__uint_as_float(f[0]), __uint_as_float(f[1])),
+                             pack_bf16(__uint_as_float(f[2]), __uint_as_float(f[3])),
+                             pack_bf16(__uint_as_float(f[4]), __uint_as_float(f[5])),
+                             pack_bf16(__uint_as_float(f[6]), __uint_as_float(f[7])));
+            }
             if (cb == 1) {
               const CUtensorMap* om = (p.out_split && nb == 1) ? &tm_o1 : (p.out_split && nb == 2) ? &tm_o2 : &tm_o0;
               issue_store(om, bf_so, ocol0, tile * 128 + q * 32);
@@ -495,17 +536,19 @@ cudaError_t launch_gemm_tc(const GemmTcArgs& a, int num_sms, cudaStream_t s, std
   p.bias = a.bias; p.relu = a.relu; p.residual = a.residual; p.res_mod = a.res_mod;
   p.out_f32 = a.out_f32; p.out_split = a.out[1] != nullptr && !a.emit_ln_g;
   p.emit_g = a.emit_ln_g; p.emit_b = a.emit_ln_b;
+  p.res_tma = (a.residual && a.res_mod == 0 && !p.prod && a.out_f32) ? 1 : 0;
   for (int j = 0; j < 3; ++j) p.out_ptr[j] = a.out[j] ? a.out[j] : a.out[0];
   if (a.emit_ln_g && !(a.out_f32 && a.N == 128 && a.out[1])) return bad("LayerNorm emit needs fp32 N == 128 output + out[1]");
   const uint32_t w_bytes = (uint32_t)(a.N / 128) * (a.K / 128) * BLK_BYTES;
   // shared-memory plan: resident W + A ring + per-warp staging slabs.  Prefer two staging slabs per
   // warp (a TMA store takes ~1 us to drain a slab) with at least two A stages; fall back to one slab.
-  const uint32_t LIMIT = 232448u, misc = 256 + 2048 + 1024;
+  const uint32_t LIMIT = 232448u, misc = 256 + 2048;
   const uint32_t stg1 = N_EPI_WARPS * STG_BYTES;
-  p.n_stg = (w_bytes + 2 * BLK_BYTES + 2 * stg1 + misc <= LIMIT) ? 2 : 1;
+  const uint32_t fixed = w_bytes + (p.res_tma ? RES_BYTES : 0u) + misc;
+  p.n_stg = (fixed + 2 * BLK_BYTES + 2 * stg1 <= LIMIT) ? 2 : 1;
   p.n_a_stages = 1;
-  while (p.n_a_stages < 3 && w_bytes + (p.n_a_stages + 1) * BLK_BYTES + p.n_stg * stg1 + misc <= LIMIT) ++p.n_a_stages;
-  const uint32_t smem = w_bytes + p.n_a_stages * BLK_BYTES + p.n_stg * stg1 + misc;
+  while (p.n_a_stages < 3 && fixed + (p.n_a_stages + 1) * BLK_BYTES + p.n_stg * stg1 <= LIMIT) ++p.n_a_stages;
+  const uint32_t smem = fixed + p.n_a_stages * BLK_BYTES + p.n_stg * stg1;
   if (smem > LIMIT) return bad("shared memory budget exceeded");
 
   CUtensorMap tw, ta, to[3];
@@ -519,6 +562,8 @@ cudaError_t launch_gemm_tc(const GemmTcArgs& a, int num_sms, cudaStream_t s, std
     void* optr = a.out[j] ? a.out[j] : a.out[0];
     if (a.emit_ln_g && j == 1)       // bf16 LayerNorm copy [M,128]
       r = make_tmap_2d(&to[j], optr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, 128, 64, 32);
+    else if (p.res_tma && j == 2)    // residual load map: 128-row boxes of 32 fp32 columns
+      r = make_tmap_2d(&to[j], a.residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, 128, 32, 128);
     else
       r = a.out_f32 ? make_tmap_2d(&to[j], optr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, ocols, 32, 32)
                     : make_tmap_2d(&to[j], optr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, ocols, 64, 32);

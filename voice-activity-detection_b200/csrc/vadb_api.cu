@@ -514,6 +514,10 @@ int vadb_forward_host(vadb_handle* h, const float* x, const int32_t* lengths, in
   int C = (int)std::max<size_t>(1, ((size_t)8 << 20) / std::max<size_t>(clip_in, 1));
   C = std::max(C, (B + 2) / 3);
   C = std::min(C, B);
+  if (const char* e = getenv("VADB_HOST_CHUNKS")) {    // tuning knob: force the number of chunks
+    const int want = atoi(e);
+    if (want >= 1) C = std::max(1, (B + want - 1) / want);
+  }
   const int n_chunks = (B + C - 1) / C;
   const size_t n = (size_t)B * T;
   auto is_pinned = [](const void* p) {
