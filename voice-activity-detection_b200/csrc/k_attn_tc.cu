@@ -38,9 +38,9 @@ using namespace tc;
 
 constexpr int BM = 128;          // query rows per tile (UMMA M)
 constexpr int BKV = 64;          // keys per K/V tile
-constexpr int NK = 4;            // K ring depth (K runs two steps ahead of V)
-constexpr int NV = 2;            // V ring depth
-constexpr int NTHREADS = 320;    // 8 softmax warps + producer + MMA
+constexpr int NK = 3;            // K ring depth (K(j+2) is requested once Q K^T(j-1) retired)
+constexpr int NV = 3;            // V ring depth (V(j) is requested once P V(j-3) retired: three steps of latency cover)
+constexpr int NTHREADS = 352;    // 8 softmax warps + TMA producer + one MMA-issuing warp per query tile
 
 constexpr uint32_t Q_HALF_BYTES = BM * 128;          // [128 rows x 64 d] bf16 = 16 KB
 constexpr uint32_t Q_TILE_BYTES = 2 * Q_HALF_BYTES;  // two d-halves
@@ -109,7 +109,25 @@ __device__ __forceinline__ Item get_item(int idx, int n_full, int npairs, int T,
   return it;
 }
 
-template <bool TRACE>
+// VAR: softmax-schedule variant bits (selected on the host, launch_attn_tc):
+//   bit 0  hand the SFU token to the other warpgroup after element EARLY_IDX of a step instead of after
+//          the last one: its barrier / LDS / first-FFMA start-up latency overlaps our last exponentials
+//   bit 1  store P in two 32-key halves: the tcgen05.st of the first half overlaps the exponentials of
+//          the second
+//   bits 2-3  fraction of the exponentials evaluated on the FMA pipe (Cody-Waite + degree-3 minimax,
+//          rel. error 7.5e-5, far below the bf16 rounding of P) instead of the SFU: 0, 1/4, 3/8, 1/2
+//   bit 4  no SFU token (the warpgroups run free)
+//   bits 5-6  element index of the early hand-over: 46, 30, 16
+#define VADB_ATTN_VARIANTS(X) X(0) X(1) X(3) X(5) X(33)
+constexpr int ATTN_DEFAULT_VARIANT = 1;
+template <int VAR> __device__ __forceinline__ bool use_poly(int i) {
+  constexpr int f = (VAR >> 2) & 3;
+  return f == 1 ? (i & 3) == 3 : f == 2 ? ((i & 7) == 1 || (i & 7) == 4 || (i & 7) == 7) : f == 3 ? (i & 1) == 1 : false;
+}
+
+template <int VAR> constexpr int early_idx() { return ((VAR >> 5) & 3) == 0 ? 46 : ((VAR >> 5) & 3) == 1 ? 30 : 16; }
+
+template <bool TRACE, int VAR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
@@ -124,11 +142,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  if (TRACE && blockIdx.x == 0 && threadIdx.x == 0 && trace) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    trace[2040] = clock64();
+    trace[2042] = (long long)gt;
+  }
   if (threadIdx.x == 0) {
     mbar_init(BAR(B_QFULL), 1);
-    mbar_init(BAR(B_QEMPTY), 1);
-    for (int s = 0; s < NK; ++s) { mbar_init(BAR(B_KFULL + s), 1); mbar_init(BAR(B_KEMPTY + s), 1); }
-    for (int s = 0; s < NV; ++s) { mbar_init(BAR(B_VFULL + s), 1); mbar_init(BAR(B_VEMPTY + s), 1); }
+    mbar_init(BAR(B_QEMPTY), 2);                 // one arrival per MMA-issuing warp
+    for (int s = 0; s < NK; ++s) { mbar_init(BAR(B_KFULL + s), 1); mbar_init(BAR(B_KEMPTY + s), 2); }
+    for (int s = 0; s < NV; ++s) { mbar_init(BAR(B_VFULL + s), 1); mbar_init(BAR(B_VEMPTY + s), 2); }
     for (int i = 0; i < 4; ++i) mbar_init(BAR(B_SFULL + i), 1);
     for (int t = 0; t < 2; ++t) {
       mbar_init(BAR(B_PFULL + t), 4);          // one arrival per softmax warp
@@ -186,14 +210,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         kc += it.nkv; vc += it.nkv;
       }
     }
-  } else if (warp == 9) {
-    // ======================= MMA issuer =======================
+  } else if (warp == 9 || warp == 10) {
+    // ======================= MMA issuers (one warp per query tile) =======================
+    // Each query tile has its own issuing warp, so the chain  P_t(j) ready -> P V_t(j), Q K^T_t(j+2)
+    // of one tile never queues behind the (blocking, tensor-pipe back-pressured) issue of the other
+    // tile; with a single issuer the pipe idled ~600 of every ~1950 cycles (profiles/r1_attention_notes.md).
     // The whole warp walks the schedule (waits included) and one elected lane issues, so the
-    // descriptor arithmetic stays warp-uniform and costs an add or two per MMA.
+    // descriptor arithmetic stays warp-uniform and costs an add or two per MMA.  The K/V/Q "empty"
+    // barriers count one arrival per issuing warp; on single-tile items the idle warp keeps the
+    // protocol uniform with plain arrivals (always behind its own wait on the matching "full" barrier,
+    // so it cannot run a phase ahead).
+    const int t = warp - 9;
     const uint32_t q_lo = desc_lo(smem_base + OFF_Q, 16);
     const uint32_t k_lo = desc_lo(smem_base + OFF_K, 16);
     const uint32_t v_lo = desc_lo(smem_base + OFF_V, KV_HALF_BYTES);   // LBO = stride between d halves
-    auto issue_qk = [&](int t, int ks, int buf) {
+    auto issue_qk = [&](int ks, int buf) {
       // S_t[buf][128 x 64] = Q_t[128 x 128] K[64 x 128]^T : 8 MMAs of K = 16 (two 64-wide d halves)
       const uint32_t qa = q_lo + (uint32_t)t * (Q_TILE_BYTES >> 4);
       const uint32_t kb = k_lo + (uint32_t)ks * (KV_TILE_BYTES >> 4);
@@ -205,7 +236,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           umma_ss_lh(d, qa + hf * (Q_HALF_BYTES >> 4) + kk * 2, kb + hf * (KV_HALF_BYTES >> 4) + kk * 2,
                      DESC_HI_SW128, IDESC_QK, (hf | kk) != 0 ? 1u : 0u);
     };
-    auto issue_pv = [&](int t, int vs, int buf, uint32_t accumulate) {
+    auto issue_pv = [&](int vs, int buf, uint32_t accumulate) {
       // O_t[128 x 128] += P_t[128 x 64] V[64 x 128] : 4 MMAs of K = 16 keys, N = 128 (two d halves);
       // P_t is read from TMEM (the head of S_t[buf]), V from shared memory
       const uint32_t pa = tmem_base + TM_S + (uint32_t)(2 * t + buf) * 64;
@@ -216,60 +247,80 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         umma_ts_lh(d, pa + kk * 8, vb + kk * (2048 >> 4), DESC_HI_SW128, IDESC_PV,
                    kk != 0 ? 1u : accumulate);
     };
+    // up to three barrier waits in parallel (lanes 0..2 spin on one barrier each): the latency of a
+    // step's formal waits is their maximum, not their sum
+    auto wait_par = [&](uint32_t b0, uint32_t p0, uint32_t b1, uint32_t p1, uint32_t b2, uint32_t p2, int n) {
+      if (lane < n) mbar_wait(lane == 0 ? b0 : lane == 1 ? b1 : b2, lane == 0 ? p0 : lane == 1 ? p1 : p2, 6);
+      __syncwarp();
+    };
     int kc = 0, vc = 0, nq = 0, n_item = 0;
-    int g[2] = {0, 0};                          // softmax steps issued so far, per query tile
+    int g = 0;                                  // softmax steps issued so far for this query tile
     for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n_item) {
       const Item it = get_item(idx, n_full, npairs, T, lengths);
       if (!it.valid || it.nkv == 0) continue;
-      const int nkv = it.nkv, ntile = it.ntile;
-      TR(0);
+      const int nkv = it.nkv;
+      const bool live = t < it.ntile;           // this warp's query tile exists in the item
+      if (t == 0) TR(0);
       mbar_wait(BAR(B_QFULL), nq & 1, 4);
       ++nq;
-      // prologue: scores of steps 0 and 1 for both query tiles
+      // prologue: scores of steps 0 and 1
       for (int j = 0; j < 2 && j < nkv; ++j) {
         const int ks = (kc + j) % NK;
         mbar_wait(BAR(B_KFULL + ks), ((kc + j) / NK) & 1, 5);
         tc_fence_after();
-        if (elect_one()) {
-          for (int t = 0; t < ntile; ++t) {
-            issue_qk(t, ks, (g[t] + j) & 1);
-            umma_commit(BAR(B_SFULL + 2 * t + ((g[t] + j) & 1)));
+        if (live) {
+          if (elect_one()) {
+            issue_qk(ks, (g + j) & 1);
+            umma_commit(BAR(B_SFULL + 2 * t + ((g + j) & 1)));
+            umma_commit(BAR(B_KEMPTY + ks));
+            if (j == nkv - 1) umma_commit(BAR(B_QEMPTY));
           }
-          umma_commit(BAR(B_KEMPTY + ks));
-          if (j == nkv - 1) umma_commit(BAR(B_QEMPTY));
+        } else if (lane == 0) {
+          mbar_arrive(BAR(B_KEMPTY + ks));
+          if (j == nkv - 1) mbar_arrive(BAR(B_QEMPTY));
         }
         __syncwarp();
       }
-      TR(1);
+      if (t == 0) TR(1);
       for (int j = 0; j < nkv; ++j) {
         const int vs = (vc + j) % NV, kn = (kc + j + 2) % NK;
         const bool more = j + 2 < nkv;
-        mbar_wait(BAR(B_VFULL + vs), ((vc + j) / NV) & 1, 6);
-        if (more) mbar_wait(BAR(B_KFULL + kn), ((kc + j + 2) / NK) & 1, 7);
-        for (int t = 0; t < ntile; ++t) {
-          TR(64 + j * 16 + t * 4 + 0);
-          mbar_wait(BAR(B_PFULL + t), (g[t] + j) & 1, 8);   // P_t(j) in smem, S_t consumed, O_t corrected
+        TR(64 + j * 16 + t * 4 + 0);
+        if (live) {
+          // V(j) and K(j+2) landed (formal: requested three steps ago; checked while P_t(j) is still
+          // being computed), then the critical wait alone: P_t(j) in TMEM (S_t consumed, O_t corrected)
+          wait_par(BAR(B_VFULL + vs), ((vc + j) / NV) & 1, BAR(B_KFULL + kn), ((kc + j + 2) / NK) & 1, 0, 0,
+                   more ? 2 : 1);
+          mbar_wait(BAR(B_PFULL + t), (g + j) & 1, 8);
           tc_fence_after();
           TR(64 + j * 16 + t * 4 + 1);
           if (elect_one()) {
-            issue_pv(t, vs, (g[t] + j) & 1, j > 0 ? 1u : 0u);
+            issue_pv(vs, (g + j) & 1, j > 0 ? 1u : 0u);
             umma_commit(BAR(B_OFULL + t));
-            if (t == ntile - 1) umma_commit(BAR(B_VEMPTY + vs));
+            umma_commit(BAR(B_VEMPTY + vs));
             if (more) {
-              issue_qk(t, kn, (g[t] + j) & 1);
-              umma_commit(BAR(B_SFULL + 2 * t + ((g[t] + j) & 1)));
-              if (t == ntile - 1) {
-                umma_commit(BAR(B_KEMPTY + kn));
-                if (j + 2 == nkv - 1) umma_commit(BAR(B_QEMPTY));   // last Q K^T of this item issued
-              }
+              issue_qk(kn, (g + j) & 1);
+              umma_commit(BAR(B_SFULL + 2 * t + ((g + j) & 1)));
+              umma_commit(BAR(B_KEMPTY + kn));
+              if (j + 2 == nkv - 1) umma_commit(BAR(B_QEMPTY));   // last Q K^T of this item issued
             }
           }
-          __syncwarp();
-          TR(64 + j * 16 + t * 4 + 3);
+        } else {
+          wait_par(BAR(B_VFULL + vs), ((vc + j) / NV) & 1, BAR(B_KFULL + kn), ((kc + j + 2) / NK) & 1, 0, 0,
+                   more ? 2 : 1);
+          if (lane == 0) {
+            mbar_arrive(BAR(B_VEMPTY + vs));
+            if (more) {
+              mbar_arrive(BAR(B_KEMPTY + kn));
+              if (j + 2 == nkv - 1) mbar_arrive(BAR(B_QEMPTY));
+            }
+          }
         }
+        __syncwarp();
+        TR(64 + j * 16 + t * 4 + 3);
       }
       kc += nkv; vc += nkv;
-      for (int t = 0; t < ntile; ++t) g[t] += nkv;
+      if (live) g += nkv;
     }
   } else {
     // ======================= softmax warpgroups =======================
@@ -303,114 +354,146 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         continue;
       }
       if (t >= it.ntile) continue;
-      const bool pingpong = it.ntile == 2;
+      const bool pingpong = it.ntile == 2 && !(VAR & 16);
       float m_ref = -CUDART_INF_F;     // reference max (log2 domain) the stored P/O are relative to
       float l_sum = 0.f;
 
-      bool s_ready = false;          // result of the poll issued one step ahead (hides the probe latency)
-      for (int j = 0; j < nkv; ++j, ++g) {
-        TS(0);
-        if (!s_ready) mbar_wait(BAR(B_SFULL + 2 * t + (g & 1)), (g >> 1) & 1, 9);
-        tc_fence_after();
-        TS(1);
+      // Software-pipelined steps.  The scores of step j+1 are pulled from TMEM into registers while the
+      // P hand-off of step j (tcgen05.st -> wait -> fence -> arrive) is still in flight, so the serial
+      // chain of a warpgroup per step is  token -> exponentials -> P store -> arrive  and nothing else;
+      // every other latency (S barrier probe, TMEM load, O barrier probe) sits in the shadow of the
+      // other warpgroup's exponentials.  One load site only (sv is written in exactly one place).
+      uint32_t sv[2][32];
+      for (int j = -1; j < nkv; ++j) {
+        const bool work = j >= 0, has_next = j + 1 < nkv;
         const uint32_t tsb = ts + (g & 1) * 64;
-        uint32_t sv[2][32];
-        tmem_ld32(tsb, sv[0]);
-        tmem_ld32(tsb + 32, sv[1]);
-        // non-blocking probes, consumed later: "P V of the previous step retired", "next S ready"
-        const bool o_ready = (j == 0) || mbar_test_wait(BAR(B_OFULL + t), (g - 1) & 1);
-        s_ready = (j + 1 < nkv) && mbar_test_wait(BAR(B_SFULL + 2 * t + ((g + 1) & 1)), ((g + 1) >> 1) & 1);
-        tmem_ld_wait();
-        TS(2);
-        const int kbase = j * BKV;
-        if (kbase + BKV > len) {                     // warp-uniform: only the last tile holds masked keys
-#pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (kbase + h2 * 32 + i >= len) sv[h2][i] = 0xFF800000u;   // -inf
-        }
-        auto row_max = [&]() {                       // 4 independent chains (one thread owns the row)
-          float mx4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(sv[0][i]), __uint_as_float(sv[0][i + 1])));
-            mx4[((i >> 1) + 2) & 3] = fmaxf(mx4[((i >> 1) + 2) & 3], fmaxf(__uint_as_float(sv[1][i]), __uint_as_float(sv[1][i + 1])));
-          }
-          return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * c;
-        };
         uint32_t pk[32];
-        float psum, p_last;
-        auto exps = [&](float m_use, bool pinned) {
-          float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+        bool o_ready = true, rescale = false;
+        if (work) {
+          TS(0);
+          // non-blocking probe, consumed after the exponentials: "P V of the previous step retired"
+          o_ready = (j == 0) || mbar_test_wait(BAR(B_OFULL + t), (g - 1) & 1);
+          const int kbase = j * BKV;
+          if (kbase + BKV > len) {                     // warp-uniform: only the last tile holds masked keys
 #pragma unroll
-          for (int i = 0; i < 64; i += 2) {
-            const float a0 = fmaf(__uint_as_float(sv[i >> 5][i & 31]), c, -m_use);
-            const float a1 = fmaf(__uint_as_float(sv[(i + 1) >> 5][(i + 1) & 31]), c, -m_use);
-            const float p0 = pinned ? fast_exp2_pinned(a0) : fast_exp2(a0);
-            const float p1 = pinned ? fast_exp2_pinned(a1) : fast_exp2(a1);
-            ps4[(i >> 1) & 3] += p0 + p1;
-            pk[i >> 1] = pack_bf16(p0, p1);
-            if (i == 62) p_last = p1;
+            for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (kbase + h2 * 32 + i >= len) sv[h2][i] = 0xFF800000u;   // -inf
           }
-          psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
-        };
-        // The exponentials of step j > 0 start from the PREVIOUS reference max (no wait for this
-        // tile's row max, which is computed alongside on otherwise idle issue slots); only if the max
-        // grew by more than 2^8 is the step redone against the new reference (rare).
-        if (j == 0) m_ref = row_max();
-        TS(3);
-        float m_use = m_ref;
-        if (pingpong) {
-          nbar_sync(t == 0 ? NB_TOKEN0 : NB_TOKEN1, 256);
-          // data dependence on a load issued after the barrier: keeps ptxas from hoisting the
-          // exponentials above the token wait
-          m_use += scratch[256];
-        }
-        exps(m_use, true);
-        const float mxl = (j == 0) ? m_ref : row_max();
-        if (pingpong) {
-          // ... and the token is handed over once the last exponential has been through the SFU (the
-          // sums / packing / row max that follow need no SFU and may trail behind the hand-over)
-          scratch[threadIdx.x] = p_last;
-          nbar_arrive(t == 0 ? NB_TOKEN1 : NB_TOKEN0, 256);
-        }
-        TS(4);
-        float alpha = 1.f;
-        const bool rescale = (j > 0) && __any_sync(0xffffffffu, mxl > m_ref + RESCALE_THRESHOLD);
-        if (rescale) {                               // warp-uniform, rare
-          const float m_new = fmaxf(m_ref, mxl);
-          alpha = fast_exp2(m_ref - m_new);
-          m_ref = m_new;
-          exps(m_ref, false);
-        }
-        l_sum = l_sum * alpha + psum;
-        // previous P V must have retired before O is rescaled (P itself lives in this step's S buffer)
-        if (rescale) {
-          if (!o_ready) mbar_wait(BAR(B_OFULL + t), (g - 1) & 1, 10);
-          tc_fence_after();
+          float psum, p_last, mxl;
+          auto exps = [&](float m_use, bool pinned) {
+            // exponentials, running sum, bf16 packing and (on otherwise idle issue slots in the shadow of
+            // the SFU) the row max of this tile, which decides about a rescale afterwards
+            float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+            float mx4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+            for (int i = 0; i < 64; i += 2) {
+              const float s0 = __uint_as_float(sv[i >> 5][i & 31]), s1 = __uint_as_float(sv[(i + 1) >> 5][(i + 1) & 31]);
+              const float a0 = fmaf(s0, c, -m_use);
+              const float a1 = fmaf(s1, c, -m_use);
+              const float p0 = use_poly<VAR>(i) ? poly_exp2(a0) : pinned ? fast_exp2_pinned(a0) : fast_exp2(a0);
+              const float p1 = use_poly<VAR>(i + 1) ? poly_exp2(a1) : pinned ? fast_exp2_pinned(a1) : fast_exp2(a1);
+              ps4[(i >> 1) & 3] += p0 + p1;
+              mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(s0, s1));
+              pk[i >> 1] = pack_bf16(p0, p1);
+              if (i == 62) p_last = p1;
+              if ((VAR & 1) && pinned && i == early_idx<VAR>() && pingpong) {
+                scratch[threadIdx.x] = p0;
+                nbar_arrive(t == 0 ? NB_TOKEN1 : NB_TOKEN0, 256);
+              }
+              if ((VAR & 2) && i == 30) tmem_st16p(tsb, pk);       // keys 0..31 of P_t
+            }
+            psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+            mxl = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * c;
+          };
+          // The exponentials of step j > 0 start from the PREVIOUS reference max; only if the max grew by
+          // more than 2^8 is the step redone against the new reference (rare).
+          if (j == 0) {
+            float mx4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(sv[0][i]), __uint_as_float(sv[0][i + 1])));
+              mx4[((i >> 1) + 2) & 3] = fmaxf(mx4[((i >> 1) + 2) & 3], fmaxf(__uint_as_float(sv[1][i]), __uint_as_float(sv[1][i + 1])));
+            }
+            m_ref = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * c;
+          }
+          TS(1);
+          float m_use = m_ref;
+          if (pingpong) {
+            nbar_sync(t == 0 ? NB_TOKEN0 : NB_TOKEN1, 256);
+            // data dependence on a load issued after the barrier: keeps ptxas from hoisting the
+            // exponentials above the token wait
+            m_use += scratch[256];
+          }
+          TS(2);
+          exps(m_use, true);
+          if (pingpong && !(VAR & 1)) {
+            // ... and the token is handed over once the last exponential has been through the SFU
+            scratch[threadIdx.x] = p_last;
+            nbar_arrive(t == 0 ? NB_TOKEN1 : NB_TOKEN0, 256);
+          }
+          TS(3);
+          float alpha = 1.f;
+          rescale = (j > 0) && __any_sync(0xffffffffu, mxl > m_ref + RESCALE_THRESHOLD);
+          if (rescale) {                               // warp-uniform, rare
+            const float m_new = fmaxf(m_ref, mxl);
+            alpha = fast_exp2(m_ref - m_new);
+            m_ref = m_new;
+            exps(m_ref, false);
+          }
+          l_sum = l_sum * alpha + psum;
+          // previous P V must have retired before O is rescaled (P itself lives in this step's S buffer)
+          if (rescale) {
+            if (!o_ready) mbar_wait(BAR(B_OFULL + t), (g - 1) & 1, 10);
+            tc_fence_after();
 #pragma unroll 1
-          for (int cb = 0; cb < 4; ++cb) {
-            uint32_t ov[32];
-            tmem_ld32(to + cb * 32, ov);
-            tmem_ld_wait();
+            for (int cb = 0; cb < 4; ++cb) {
+              uint32_t ov[32];
+              tmem_ld32(to + cb * 32, ov);
+              tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-            tmem_st32(to + cb * 32, ov);
+              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+              tmem_st32(to + cb * 32, ov);
+            }
           }
+          if (VAR & 2) tmem_st16p(tsb + 16, pk + 16);  // keys 32..63 (the first half went out mid-step)
+          else tmem_st32(tsb, pk);                     // P_t (bf16 pairs) over the head of S_t[buf]
+          TS(4);
         }
-        TS(5);
-        tmem_st32(tsb, pk);                          // P_t (bf16 pairs) over the head of S_t[buf]
-        // An mbarrier may run at most one phase ahead of its waiter: do not signal P_t(j) before the
-        // MMA warp has consumed P_t(j-1) (it has once P V(j-1) retired).  The probe was issued at the
-        // top of the step, so this is normally free.
-        if (!o_ready && !rescale) mbar_wait(BAR(B_OFULL + t), (g - 1) & 1, 12);
-        tmem_st_wait();
-        TS(6);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_PFULL + t));
-        TS(7);
+        // scores of the next step: TMEM -> registers.  If they are already there the load is issued now and
+        // its latency overlaps the P hand-off; if not, P is handed over first (it must never wait for S:
+        // the MMA warp needs P_t(j) to get to Q K^T(j+2)) and the scores are awaited afterwards.
+        const int gn = work ? g + 1 : g;
+        const uint32_t tsn = ts + (gn & 1) * 64;
+        bool s_loaded = false;
+        if (has_next && work && mbar_test_wait(BAR(B_SFULL + 2 * t + (gn & 1)), (gn >> 1) & 1)) {
+          tc_fence_after();
+          tmem_ld32(tsn, sv[0]);
+          tmem_ld32(tsn + 32, sv[1]);
+          s_loaded = true;
+        }
+        if (work) {
+          TS(5);
+          // An mbarrier may run at most one phase ahead of its waiter: do not signal P_t(j) before the
+          // MMA warp has consumed P_t(j-1) (it has once P V(j-1) retired).  The probe was issued at the
+          // top of the step, so this is normally free.
+          if (!o_ready && !rescale) mbar_wait(BAR(B_OFULL + t), (g - 1) & 1, 12);
+          tmem_st_wait();
+          TS(6);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_PFULL + t));
+          ++g;
+        }
+        if (has_next && !s_loaded) {
+          mbar_wait(BAR(B_SFULL + 2 * t + (gn & 1)), (gn >> 1) & 1, 9);
+          tc_fence_after();
+          tmem_ld32(tsn, sv[0]);
+          tmem_ld32(tsn + 32, sv[1]);
+        }
+        if (has_next) tmem_ld_wait();
+        if (work) TS(7);
       }
 
       // epilogue: O_t / l -> bf16 -> two 128B-swizzled staging tiles (64 columns each) -> TMA stores in
@@ -434,10 +517,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         for (int ch = 0; ch < 8; ++ch) {
           uint4 o4;
           const uint32_t* src = &ov[ch >> 2][(ch & 3) * 8];
-          o4.x = pack_bf16(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
-          o4.y = pack_bf16(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
-          o4.z = pack_bf16(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
-          o4.w = pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+          o4.x = pack_bf16_alu(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+          o4.y = pack_bf16_alu(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+          o4.z = pack_bf16_alu(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+          o4.w = pack_bf16_alu(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
           *reinterpret_cast<uint4*>(ost + hf * P_TILE_BYTES + sw128_offset(row, ch)) = o4;
         }
       }
@@ -460,6 +543,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+  if (TRACE && blockIdx.x == 0 && threadIdx.x == 0 && trace) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    trace[2041] = clock64();
+    trace[2043] = (long long)gt;
   }
 }
 
@@ -535,50 +624,59 @@ cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o,
     if (n_pairs > grid && rem > 0 && 2 * rem <= grid) { n_full = n_pairs - rem; n_items = n_full + 2 * rem; }
   }
   static const bool want_trace = getenv("VADB_ATTN_TRACE") != nullptr;
-  if (want_trace) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)SMEM_ALLOC);
-    if (e != cudaSuccess) return e;
-    long long* dtrace = nullptr;
-    const int NTR = 2048;
-    cudaMalloc(&dtrace, NTR * sizeof(long long));
-    cudaMemsetAsync(dtrace, 0, NTR * sizeof(long long), s);
-    attn_tc_kernel<true><<<(unsigned)grid, NTHREADS, SMEM_ALLOC, s>>>(tq, tk, tv, to, o, lengths, T, npairs, n_items, n_full, dtrace);
-    std::vector<long long> ht(NTR);
-    cudaMemcpyAsync(ht.data(), dtrace, NTR * sizeof(long long), cudaMemcpyDeviceToHost, s);
-    cudaStreamSynchronize(s);
-    cudaFree(dtrace);
-    const long long t0 = ht[0];
-    auto rel = [&](int i) { return ht[i] ? (long long)(ht[i] - t0) : -1LL; };
-    fprintf(stderr, "[attn trace] mma: start=0 prologue issued=%lld  end(sync)=%lld\n", rel(1), rel(2));
-    const int nkv = (T + BKV - 1) / BKV;
-    for (int j = 0; j < nkv && j < 16; ++j) {
-      fprintf(stderr, "[attn trace] j=%d mma t0: waitP %lld->%lld issued %lld | t1: waitP %lld->%lld issued %lld\n", j,
-              rel(64 + j * 16 + 0), rel(64 + j * 16 + 1), rel(64 + j * 16 + 3),
-              rel(64 + j * 16 + 4), rel(64 + j * 16 + 5), rel(64 + j * 16 + 7));
-      for (int t = 0; t < 2; ++t) {
-        const int b0 = 512 + j * 32 + t * 16;
-        fprintf(stderr, "[attn trace]   sm%d: waitS %lld->%lld ld %lld max %lld exp %lld waitO %lld corr+sts %lld arrive %lld\n",
-                t, rel(b0 + 0), rel(b0 + 1), rel(b0 + 2), rel(b0 + 3), rel(b0 + 4), rel(b0 + 5), rel(b0 + 6),
-                rel(b0 + 7));
+  static const int variant = getenv("VADB_ATTN_VARIANT") ? atoi(getenv("VADB_ATTN_VARIANT")) : ATTN_DEFAULT_VARIANT;
+  auto run = [&](auto kern_trace, auto kern) -> cudaError_t {
+    if (want_trace) {
+      cudaError_t e = cudaFuncSetAttribute(kern_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
+      if (e != cudaSuccess) return e;
+      long long* dtrace = nullptr;
+      const int NTR = 2048;
+      cudaMalloc(&dtrace, NTR * sizeof(long long));
+      cudaMemsetAsync(dtrace, 0, NTR * sizeof(long long), s);
+      kern_trace<<<(unsigned)grid, NTHREADS, SMEM_ALLOC, s>>>(tq, tk, tv, to, o, lengths, T, npairs, n_items, n_full, dtrace);
+      std::vector<long long> ht(NTR);
+      cudaMemcpyAsync(ht.data(), dtrace, NTR * sizeof(long long), cudaMemcpyDeviceToHost, s);
+      cudaStreamSynchronize(s);
+      cudaFree(dtrace);
+      const long long t0 = ht[0];
+      auto rel = [&](int i) { return ht[i] ? (long long)(ht[i] - t0) : -1LL; };
+      fprintf(stderr, "[attn trace] variant %d: mma start=0 prologue issued=%lld\n", variant, rel(1));
+      // CTA 0, whole kernel: clock64 and globaltimer at entry / exit -> SM clock and cycles per CTA
+      if (ht[2043] > ht[2042])
+        fprintf(stderr, "[attn trace] CTA0 lifetime: %lld cycles, %lld ns -> %.0f MHz; item 1 started at cycle %lld\n",
+                ht[2041] - ht[2040], ht[2043] - ht[2042], 1e3 * (double)(ht[2041] - ht[2040]) / (double)(ht[2043] - ht[2042]),
+                t0 - ht[2040]);
+      const int nkv = (T + BKV - 1) / BKV;
+      for (int j = 0; j < nkv && j < 16; ++j) {
+        fprintf(stderr, "[attn trace] j=%d mma t0: waitP %lld->%lld issued %lld | t1: waitP %lld->%lld issued %lld\n", j,
+                rel(64 + j * 16 + 0), rel(64 + j * 16 + 1), rel(64 + j * 16 + 3),
+                rel(64 + j * 16 + 4), rel(64 + j * 16 + 5), rel(64 + j * 16 + 7));
+        for (int t = 0; t < 2; ++t) {
+          const int b0 = 512 + j * 32 + t * 16;
+          fprintf(stderr, "[attn trace]   sm%d: waitS %lld->%lld ld %lld max %lld exp %lld waitO %lld corr+sts %lld arrive %lld\n",
+                  t, rel(b0 + 0), rel(b0 + 1), rel(b0 + 2), rel(b0 + 3), rel(b0 + 4), rel(b0 + 5), rel(b0 + 6),
+                  rel(b0 + 7));
+        }
       }
+      for (int t = 0; t < 2; ++t)
+        fprintf(stderr, "[attn trace] epilogue t%d: waitO %lld->%lld done %lld\n", t, rel(32 + t * 4), rel(32 + t * 4 + 1),
+                rel(32 + t * 4 + 2));
+      return cudaGetLastError();
     }
-    for (int t = 0; t < 2; ++t)
-      fprintf(stderr, "[attn trace] epilogue t%d: waitO %lld->%lld done %lld\n", t, rel(32 + t * 4), rel(32 + t * 4 + 1),
-              rel(32 + t * 4 + 2));
-    return cudaGetLastError();
-  }
-  static thread_local int attr_dev = -1;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (attr_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)SMEM_ALLOC);
+    // the attribute is per function and per device; setting it on every launch costs ~1 us of host time
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
     if (e != cudaSuccess) return e;
-    attr_dev = dev;
+    kern<<<(unsigned)grid, NTHREADS, SMEM_ALLOC, s>>>(tq, tk, tv, to, o, lengths, T, npairs, n_items, n_full, nullptr);
+    return cudaGetLastError();
+  };
+  switch (variant) {
+#define VADB_ATTN_CASE(V) case V: return run(attn_tc_kernel<true, V>, attn_tc_kernel<false, V>);
+    VADB_ATTN_VARIANTS(VADB_ATTN_CASE)
+#undef VADB_ATTN_CASE
+    default:
+      if (err) *err = "unknown VADB_ATTN_VARIANT " + std::to_string(variant);
+      return cudaErrorInvalidValue;
   }
-  attn_tc_kernel<false><<<(unsigned)grid, NTHREADS, SMEM_ALLOC, s>>>(tq, tk, tv, to, o, lengths, T, npairs, n_items, n_full, nullptr);
-  return cudaGetLastError();
 }
 
 }  // namespace vadb

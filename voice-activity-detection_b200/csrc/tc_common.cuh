@@ -247,6 +247,16 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         "r"(v[14]), "r"(v[15])
       : "memory");
 }
+// Same from a pointer into a register array (indices are compile-time constants after inlining).
+__device__ __forceinline__ void tmem_st16p(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+        "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]),
+        "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -271,6 +281,19 @@ __device__ __forceinline__ float fast_exp2_pinned(float x) {
   return y;
 }
 
+// 2^x on the FMA pipe (no SFU): round-to-nearest split x = n + f with the 1.5*2^23 magic constant,
+// degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5), exponent inserted
+// by an integer add.  Arguments below -125 are clamped (result ~2e-38, i.e. zero for softmax).
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.05517197400331497f, 0.2426111400127411f);
+  p = fmaf(p, f, 0.693260908126831f);
+  p = fmaf(p, f, 0.9999280571937561f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
+
 // Write a warp's staged [32 rows x 128 B] slab (128B-swizzled, see sw128_offset) to global memory with
 // fully coalesced 16-byte stores: each instruction covers 4 rows x 128 B = 4 whole lines.  Plain stores
 // retire without a completion wait, so one slab per warp is enough.
@@ -290,6 +313,13 @@ __device__ __forceinline__ void store_slab(const unsigned char* stg, unsigned ch
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Same packing on the integer ALU: cvt.rn.bf16x2.f32 (F2FP) issues once per ~9 cycles per SM sub-partition on
+// B200 (tools/ubench/explab.cu), two IADDs and a PRMT issue at full rate.  Rounds to nearest with ties
+// away from zero (cvt rounds ties to even): the results differ only on exact ties.
+__device__ __forceinline__ uint32_t pack_bf16_alu(float lo, float hi) {
+  return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
 }
 
 }  // namespace tc
