@@ -144,6 +144,37 @@ def test_attention_kernel(B, T, masked, dtype, tol):
     assert err <= tol
 
 
+@pytest.mark.parametrize("T", [1, 2, 3, 5, 7, 8])
+@pytest.mark.parametrize("B,masked", [(1, False), (2, False), (37, True), (1001, True)])
+def test_attention_small_T_kernel(B, T, masked):
+    """T <= 8 (the reference Predictor's 7-frame windows, vad/predictor.py:57-59) runs on the dedicated
+    warp-per-window-pair kernel: odd / even window counts, every T, ragged lengths, and agreement with
+    the tcgen05 kernel's tolerance."""
+    eng = engine_for(SYN, "bf16")
+    g = torch.Generator().manual_seed(B * 100 + T)
+    q = (torch.randn(B, T, 128, generator=g) * 1.5).to(torch.bfloat16).cuda()
+    k = (torch.randn(B, T, 128, generator=g) * 1.5).to(torch.bfloat16).cuda()
+    v = torch.randn(B, T, 128, generator=g).to(torch.bfloat16).cuda()
+    lengths = None
+    if masked:
+        lengths = torch.randint(1, T + 1, (B,), generator=g).to(torch.int32).cuda()
+        lengths[0] = T
+    o = eng.attention(q, k, v, lengths)
+    want = _ref_attention(q, k, v, lengths)
+    err = (o.double() - want).abs()
+    print(f"small attn B={B} T={T} masked={masked}: {err.max().item():.3e}")
+    assert torch.isfinite(o).all()
+    # bf16 P (2^-9 of sum p|v|, |v| reaches 4-5 here) and bf16 output rounding (2^-9 of |o|)
+    assert (err <= 1e-2 + 8e-3 * want.abs()).all()
+
+
+def test_attention_small_T_fully_masked_window_is_nan():
+    eng = engine_for(SYN, "bf16")
+    q = torch.randn(3, 7, 128).to(torch.bfloat16).cuda()
+    o = eng.attention(q, q, q, torch.tensor([7, 0, 3], dtype=torch.int32).cuda())
+    assert torch.isfinite(o[0]).all() and torch.isnan(o[1]).all() and torch.isfinite(o[2]).all()
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_attention_online_softmax_rescale(dtype):
     """Scores that grow along the key axis force the running max to move in every KV tile."""

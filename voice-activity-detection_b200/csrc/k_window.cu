@@ -34,6 +34,48 @@ __global__ void boost_kernel(const float* __restrict__ prob_nW, int L, int half,
   }
 }
 
+// Window gather AFTER the input projection.  The input layer is a per-frame Linear
+// (vad/models/self_attention.py:12-16), so the [L, F] clip is projected once and the W-fold overlapping
+// context windows (vad/predictor.py:182-218) are assembled from the projected rows: row m = i*W + k of
+// the model input is  proj[half + i + rel[k]] + PE[k]/sqrt(d)  (the window is the model's whole sequence,
+// so its positional slot is k).  One warp per output row: 512 B gathered (L2-resident: the projected
+// clip is W-fold reused), residual row written in fp32 and LayerNorm_1 of layer 0 emitted in bf16 for
+// the first Q/K/V GEMM -- the same two outputs the front-end GEMM produces on the clip path.
+__global__ void __launch_bounds__(256)
+window_gather_ln_kernel(const float* __restrict__ proj, const float* __restrict__ pe, float* __restrict__ out_h,
+                        bf16* __restrict__ out_ln, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                        long n_rows, int W, int half, int jump) {
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long n_warps = ((long)gridDim.x * blockDim.x) >> 5;
+  const float4 gam = __ldg(reinterpret_cast<const float4*>(ln_g) + lane);
+  const float4 bet = __ldg(reinterpret_cast<const float4*>(ln_b) + lane);
+  for (long m = warp; m < n_rows; m += n_warps) {
+    const long i = m / W;
+    const int k = (int)(m - i * W);
+    const long src = half + i + rel_of_slot(k, half, jump);
+    float4 v = __ldg(reinterpret_cast<const float4*>(proj + src * D) + lane);
+    const float4 e = __ldg(reinterpret_cast<const float4*>(pe + (long)k * D) + lane);
+    v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+    __stcs(reinterpret_cast<float4*>(out_h + m * D) + lane, v);
+    float sum = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / D);
+    const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+    float sq = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.0f / D) + LN_EPS);       // biased variance, eps 1e-5 (nn.LayerNorm)
+    __nv_bfloat162 lo = __floats2bfloat162_rn(dx * rstd * gam.x + bet.x, dy * rstd * gam.y + bet.y);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(dz * rstd * gam.z + bet.z, dw * rstd * gam.w + bet.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    __stcs(reinterpret_cast<uint2*>(out_ln + m * D) + lane, pk);
+  }
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
   size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
@@ -63,6 +105,16 @@ __global__ void pad_rows_bf16_kernel(const float* __restrict__ in, bf16* __restr
 
 cudaError_t launch_pad_rows_bf16(const float* in, bf16* out, int rows, int cols, cudaStream_t s) {
   pad_rows_bf16_kernel<<<(rows * 128 + 255) / 256, 256, 0, s>>>(in, out, rows, cols);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_window_gather_ln(const float* proj, const float* pe, float* out_h, bf16* out_ln,
+                                    const float* ln_g, const float* ln_b, long n_rows, int W, int half,
+                                    int jump, cudaStream_t s) {
+  if (n_rows <= 0) return cudaSuccess;
+  long blocks = (n_rows + 7) / 8;                 // 8 warps (rows) per block per pass
+  if (blocks > 148 * 8) blocks = 148 * 8;         // a multiple of the SM count; warps then stride over rows
+  window_gather_ln_kernel<<<(unsigned)blocks, 256, 0, s>>>(proj, pe, out_h, out_ln, ln_g, ln_b, n_rows, W, half, jump);
   return cudaGetLastError();
 }
 

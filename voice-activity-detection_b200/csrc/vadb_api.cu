@@ -2,6 +2,7 @@
 // orchestration of the forward pass / predictor window path on a caller-provided stream.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -80,6 +81,7 @@ struct vadb_handle {
   void* dev_out = nullptr; size_t dev_out_bytes = 0;
   int32_t* dev_len = nullptr; size_t dev_len_n = 0;
   void* win_prob = nullptr; size_t win_prob_bytes = 0;   // [n, W] per-window probabilities
+  void* win_proj = nullptr; size_t win_proj_bytes = 0;   // [L, 128] fp32 input projection of the whole clip
 };
 
 namespace {
@@ -180,7 +182,12 @@ int gemm_tc(vadb_handle* h, const GemmTcArgs& a, cudaStream_t s) {
 
 int attention(vadb_handle* h, const void* q, const void* k, const void* v, void* o, int dtype,
               const int32_t* lengths, int B, int T, cudaStream_t s) {
-  if (dtype == VADB_BF16) {
+  static const bool small_ok = !(getenv("VADB_ATTN_SMALL") && atoi(getenv("VADB_ATTN_SMALL")) == 0);
+  if (dtype == VADB_BF16 && small_ok && attn_small_supported(T)) {
+    // the reference Predictor's 7-frame windows: a 128-row tcgen05 tile would be 94 % padding
+    cudaError_t e = launch_attn_small((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, lengths, B, T, s);
+    if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("attn_small: ") + cudaGetErrorString(e));
+  } else if (dtype == VADB_BF16) {
     std::string err;
     cudaError_t e = launch_attn_tc((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, lengths,
                                    B, T, s, &err);
@@ -402,6 +409,7 @@ void vadb_destroy(vadb_handle* h) {
   if (h->dev_out) cudaFree(h->dev_out);
   if (h->dev_len) cudaFree(h->dev_len);
   if (h->win_prob) cudaFree(h->win_prob);
+  if (h->win_proj) cudaFree(h->win_proj);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->own_stream2) cudaStreamDestroy(h->own_stream2);
   for (int i = 0; i < 2; ++i) {
@@ -607,11 +615,34 @@ int vadb_predict_probabilities(vadb_handle* h, const float* feat, int L, int hal
     size_t need = (size_t)n * W * sizeof(float);
     if ((rc = ensure_bytes(h, &h->win_prob, &h->win_prob_bytes, need, false))) return rc;
     prob_all = (float*)h->win_prob;
+    // bf16 mode: project-then-gather.  The input Linear is per frame, so the L frames are projected
+    // once (tensor cores) and each window row is proj[src] + PE[slot]: W times fewer MMAs and no
+    // register-staged gather inside the GEMM.  fp32 mode keeps the gather folded into the GEMM.
+    static const bool ptg_ok = !(getenv("VADB_WINDOW_PTG") && atoi(getenv("VADB_WINDOW_PTG")) == 0);
+    const bool ptg = ptg_ok && is_bf16_mode(h) && F <= D && F % 4 == 0 && (reinterpret_cast<uintptr_t>(feat) % 16) == 0;
+    if (ptg) {
+      if ((rc = ensure_bytes(h, &h->win_proj, &h->win_proj_bytes, (size_t)L * D * sizeof(float), false))) return rc;
+      GemmTcArgs g = {};
+      g.M = L; g.N = D; g.K = D; g.w_bf16 = h->win_bf;
+      g.a_rows = feat; g.a_cols = F; g.a_rows_bf16 = 0;
+      g.bias = h->w32 + h->lay.b_in;
+      g.out_f32 = 1; g.out[0] = h->win_proj;
+      if ((rc = gemm_tc(h, g, s))) return rc;
+    }
     for (int c0 = 0; c0 < n; c0 += wpp) {
       const int nc = std::min(wpp, n - c0);
-      // window gather folded into the front-end GEMM's A-row index (vad/predictor.py:182-218);
-      // the positional slot of row m is m % W (the window is the model's whole sequence)
-      if ((rc = front_end(h, feat + (size_t)c0 * F, 0, nc * W, W, W, half, jump, s))) return rc;
+      if (ptg) {
+        cudaError_t e = launch_window_gather_ln((const float*)h->win_proj + (size_t)c0 * D, h->pe, h->ws_h, h->ws_aln,
+                                                h->w32 + h->lay.layers[0].ln1_g, h->w32 + h->lay.layers[0].ln1_b,
+                                                (long)nc * W, W, half, jump, s);
+        if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("window gather: ") + cudaGetErrorString(e));
+        h->aln_valid = true;
+        h->launches++;
+      } else {
+        // window gather folded into the front-end GEMM's A-row index (vad/predictor.py:182-218);
+        // the positional slot of row m is m % W (the window is the model's whole sequence)
+        if ((rc = front_end(h, feat + (size_t)c0 * F, 0, nc * W, W, W, half, jump, s))) return rc;
+      }
       if ((rc = run_encoder(h, nullptr, nc, W, prob_all + (size_t)c0 * W, nullptr, s))) return rc;
     }
     cudaError_t e = launch_boost(prob_all, L, half, jump, W, probs_LW, mean_L, s);

@@ -65,6 +65,12 @@ cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o,
                            const int32_t* lengths, int B, int T, cudaStream_t s,
                            std::string* err);
 
+// bf16 attention for T <= 8 (the 7-frame windows of the reference Predictor): one warp per pair of
+// windows on mma.sync, no shared memory (k_attn_small.cu)
+bool attn_small_supported(int T);
+cudaError_t launch_attn_small(const bf16* q, const bf16* k, const bf16* v, bf16* o,
+                              const int32_t* lengths, int B, int T, cudaStream_t s);
+
 // tcgen05 GEMM for the per-frame Linears in bf16 mode (k_gemm_tc.cu)
 struct GemmTcArgs {
   int M, N, K;
@@ -110,6 +116,11 @@ cudaError_t launch_classifier(const float* h, const float* g, const float* b, co
 // window path helpers (k_window.cu)
 cudaError_t launch_boost(const float* prob_nW, int L, int half, int jump, int W,
                          float* probs_LW, float* mean_L, cudaStream_t s);
+
+// rows of the projected clip gathered into context windows + PE + LayerNorm_1 emit (k_window.cu)
+cudaError_t launch_window_gather_ln(const float* proj, const float* pe, float* out_h, bf16* out_ln,
+                                    const float* ln_g, const float* ln_b, long n_rows, int W, int half,
+                                    int jump, cudaStream_t s);
 
 // misc element-wise (k_window.cu)
 cudaError_t launch_pad_rows_bf16(const float* in, bf16* out, int rows, int cols, cudaStream_t s);
