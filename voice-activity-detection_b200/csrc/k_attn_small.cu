@@ -42,7 +42,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint3
 }
 __device__ __forceinline__ uint4 ldg_nc16(const void* p) {
   uint4 v;
-  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
@@ -66,6 +66,8 @@ __device__ __forceinline__ float quad_sum(float v) {
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 attn_small_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K, const bf16* __restrict__ V,
                   bf16* __restrict__ O, const int32_t* __restrict__ lengths, int n_win, int T) {
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int warp_global = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -198,8 +200,7 @@ cudaError_t launch_attn_small(const bf16* q, const bf16* k, const bf16* v, bf16*
   const long want = ((long)n_pairs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
   const long cap = (long)num_sms * 16;            // 64 warps per SM; each warp then loops over its pairs
   const unsigned grid = (unsigned)(want < cap ? want : cap);
-  attn_small_kernel<<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(q, k, v, o, lengths, B, T);
-  return cudaGetLastError();
+  return launch_k(attn_small_kernel, grid, WARPS_PER_BLOCK * 32, 0, s, q, k, v, o, lengths, B, T);
 }
 
 }  // namespace vadb

@@ -172,6 +172,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();                 // the set-up above overlaps the previous kernel's tail (vadb_common.cuh)
 
   if (warp == 8) {
     // ======================= TMA producer =======================
@@ -666,8 +668,8 @@ cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o,
     // the attribute is per function and per device; setting it on every launch costs ~1 us of host time
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)grid, NTHREADS, SMEM_ALLOC, s>>>(tq, tk, tv, to, o, lengths, T, npairs, n_items, n_full, nullptr);
-    return cudaGetLastError();
+    return launch_k(kern, (unsigned)grid, NTHREADS, SMEM_ALLOC, s, tq, tk, tv, to, o, lengths, T, npairs, n_items, n_full,
+                    (long long*)nullptr);
   };
   switch (variant) {
 #define VADB_ATTN_CASE(V) case V: return run(attn_tc_kernel<true, V>, attn_tc_kernel<false, V>);

@@ -24,12 +24,14 @@ __global__ void __launch_bounds__(256) classifier_kernel(const float* __restrict
   const float4 w0 = __ldg(reinterpret_cast<const float4*>(wc) + lane);
   const float4 w1 = __ldg(reinterpret_cast<const float4*>(wc + D) + lane);
   const float b0 = __ldg(bc), b1 = __ldg(bc + 1);
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();                 // weights above, activations below (vadb_common.cuh)
   // four rows per warp iteration: four independent 512-byte row loads in flight per warp
   for (long row0 = warp * 4; row0 < M; row0 += nwarps * 4) {
     float4 xr[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      xr[u] = (row0 + u < M) ? __ldg(reinterpret_cast<const float4*>(h + (row0 + u) * D) + lane)
+      xr[u] = (row0 + u < M) ? __ldcg(reinterpret_cast<const float4*>(h + (row0 + u) * D) + lane)
                              : make_float4(0.f, 0.f, 0.f, 0.f);
     float st[4];
 #pragma unroll
@@ -86,7 +88,7 @@ cudaError_t launch_classifier(const float* h, const float* g, const float* b, co
   const int warps_per_block = 8;
   long blocks = ((long)M + 4 * warps_per_block - 1) / (4 * warps_per_block);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  classifier_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(h, g, b, wc, bc, M, prob, logp);
+  { cudaError_t e = launch_k(classifier_kernel, (unsigned)blocks, warps_per_block * 32, 0, s, h, g, b, wc, bc, M, prob, logp); if (e != cudaSuccess) return e; }
   return cudaGetLastError();
 }
 

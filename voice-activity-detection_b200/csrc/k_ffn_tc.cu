@@ -111,6 +111,8 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();                 // the set-up above overlaps the previous kernel's tail (vadb_common.cuh)
 
   if (warp == 0) {
     // ======================= weight streamer =======================
@@ -367,7 +369,7 @@ cudaError_t launch_ffn_tc(const FfnTcArgs& a, int num_sms, cudaStream_t s, std::
   }
   const int n_tiles = (a.M + 127) / 128;
   const int grid = n_tiles < num_sms ? n_tiles : num_sms;
-  ffn_tc_kernel<<<grid, NTHREADS, SMEM_ALLOC, s>>>(t1, t2, ta, to, te, p);
+  { cudaError_t e = launch_k(ffn_tc_kernel, grid, NTHREADS, SMEM_ALLOC, s, t1, t2, ta, to, te, p); if (e != cudaSuccess) return e; }
   return cudaGetLastError();
 }
 

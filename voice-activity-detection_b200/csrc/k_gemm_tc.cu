@@ -146,6 +146,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: the set-up above and the weight loads below do not depend on the previous kernel; everything
+  // that touches activations comes after pdl_wait()
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  if (!(warp == 0 && lane == 0)) pdl_wait();
 
   if (warp == 0) {
     // ======================= TMA producer =======================
@@ -156,6 +160,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
           for (int hf = 0; hf < 2; ++hf)
             tma_load_2d(smem_base + off_w + (uint32_t)(nb * KC + kc) * BLK_BYTES + hf * HALF_BYTES, &tm_w,
                         BAR(BAR_WFULL), kc * 128 + hf * 64, nb * 128);
+      pdl_wait();
       if (!p.prod) {
         int ac = 0, n = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
@@ -614,8 +619,8 @@ cudaError_t launch_gemm_tc(const GemmTcArgs& a, int num_sms, cudaStream_t s, std
     if (e != cudaSuccess) return e;
     attr_dev[p.prod ? 1 : 0] = dev;
   }
-  if (p.prod) gemm_tc_kernel<false, true><<<grid, NTHREADS, smem, s>>>(tw, ta, to[0], to[1], to[2], p, nullptr);
-  else gemm_tc_kernel<false, false><<<grid, NTHREADS - 128, smem, s>>>(tw, ta, to[0], to[1], to[2], p, nullptr);
+  if (p.prod) return launch_k(gemm_tc_kernel<false, true>, grid, NTHREADS, smem, s, tw, ta, to[0], to[1], to[2], p, (long long*)nullptr);
+  return launch_k(gemm_tc_kernel<false, false>, grid, NTHREADS - 128, smem, s, tw, ta, to[0], to[1], to[2], p, (long long*)nullptr);
   return cudaGetLastError();
 }
 

@@ -21,12 +21,14 @@ __device__ __forceinline__ int rel_of_slot(int k, int half, int jump) {
 __global__ void boost_kernel(const float* __restrict__ prob_nW, int L, int half, int jump, int W,
                              float* __restrict__ probs_LW, float* __restrict__ mean_L) {
   const int n = L - 2 * half;
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
   for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < L;
        p += (long)gridDim.x * blockDim.x) {
     float sum = 0.f;
     for (int k = 0; k < W; ++k) {
       const long i = p - half - rel_of_slot(k, half, jump);
-      const float v = (i >= 0 && i < n) ? __ldg(prob_nW + i * W + k) : 0.5f;
+      const float v = (i >= 0 && i < n) ? __ldcg(prob_nW + i * W + k) : 0.5f;
       if (probs_LW) probs_LW[p * W + k] = v;
       sum += v;
     }
@@ -50,11 +52,13 @@ window_gather_ln_kernel(const float* __restrict__ proj, const float* __restrict_
   const long n_warps = ((long)gridDim.x * blockDim.x) >> 5;
   const float4 gam = __ldg(reinterpret_cast<const float4*>(ln_g) + lane);
   const float4 bet = __ldg(reinterpret_cast<const float4*>(ln_b) + lane);
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
   for (long m = warp; m < n_rows; m += n_warps) {
     const long i = m / W;
     const int k = (int)(m - i * W);
     const long src = half + i + rel_of_slot(k, half, jump);
-    float4 v = __ldg(reinterpret_cast<const float4*>(proj + src * D) + lane);
+    float4 v = *(reinterpret_cast<const float4*>(proj + src * D) + lane);     // written by the previous kernel
     const float4 e = __ldg(reinterpret_cast<const float4*>(pe + (long)k * D) + lane);
     v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
     __stcs(reinterpret_cast<float4*>(out_h + m * D) + lane, v);
@@ -114,8 +118,7 @@ cudaError_t launch_window_gather_ln(const float* proj, const float* pe, float* o
   if (n_rows <= 0) return cudaSuccess;
   long blocks = (n_rows + 7) / 8;                 // 8 warps (rows) per block per pass
   if (blocks > 148 * 8) blocks = 148 * 8;         // a multiple of the SM count; warps then stride over rows
-  window_gather_ln_kernel<<<(unsigned)blocks, 256, 0, s>>>(proj, pe, out_h, out_ln, ln_g, ln_b, n_rows, W, half, jump);
-  return cudaGetLastError();
+  return launch_k(window_gather_ln_kernel, (unsigned)blocks, 256, 0, s, proj, pe, out_h, out_ln, ln_g, ln_b, n_rows, W, half, jump);
 }
 
 cudaError_t launch_boost(const float* prob_nW, int L, int half, int jump, int W, float* probs_LW,
@@ -123,8 +126,7 @@ cudaError_t launch_boost(const float* prob_nW, int L, int half, int jump, int W,
   if (L <= 0) return cudaSuccess;
   int blocks = (L + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  boost_kernel<<<blocks, 256, 0, s>>>(prob_nW, L, half, jump, W, probs_LW, mean_L);
-  return cudaGetLastError();
+  return launch_k(boost_kernel, blocks, 256, 0, s, prob_nW, L, half, jump, W, probs_LW, mean_L);
 }
 
 cudaError_t launch_f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t s) {

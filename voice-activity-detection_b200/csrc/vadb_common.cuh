@@ -17,6 +17,31 @@ constexpr float LN_EPS = 1e-5f;
 
 typedef __nv_bfloat16 bf16;
 
+// ---------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  One forward is 14 back-to-back kernels, most of them persistent
+// one-CTA-per-SM grids whose prologue (mbarrier init, TMEM allocation, tensor-map fetch, weight loads)
+// does not depend on the previous kernel.  Every kernel is launched with the programmatic-stream-
+// serialization attribute: its CTAs may start as soon as all CTAs of the previous kernel have called
+// pdl_launch_dependents() (first thing they do) and an SM has room, run their prologue, and block in
+// pdl_wait() until the previous grid has completed and its memory is visible.  Nothing produced by an
+// earlier kernel may be touched before pdl_wait().  VADB_PDL=0 falls back to plain stream order.
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // Offsets (in floats) of every tensor inside the packed fp32 blob; order == state_dict order.
 struct LayerOffsets {
   size_t wq, bq, wk, bk, wv, bv, wo, bo, ln1_g, ln1_b, w1, b1, w2, b2, ln2_g, ln2_b;
