@@ -53,6 +53,13 @@ struct FfnParams {
   bf16* emit_out;
   const float* b1;       // [512]
   const float* b2;       // [128]
+  // last layer: final LayerNorm + classifier + log-softmax fused into the epilogue (h is not stored)
+  const float* cls_g;    // [128] final LayerNorm gamma, nullptr -> not the last layer
+  const float* cls_b;    // [128]
+  const float* cls_w;    // [2,128] classifier weight
+  const float* cls_bias; // [2]
+  float* prob;           // [M] or nullptr
+  float* logp;           // [M,2] or nullptr
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
@@ -270,13 +277,63 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__
           const uint32_t* s4 = &v[cb][c4 * 4];
           const float4 f4 = make_float4(__uint_as_float(s4[0]) + b4.x + r4.x, __uint_as_float(s4[1]) + b4.y + r4.y,
                                         __uint_as_float(s4[2]) + b4.z + r4.z, __uint_as_float(s4[3]) + b4.w + r4.w);
-          *cell = f4;
+          if (!p.cls_g) *cell = f4;
           v[cb][c4 * 4] = __float_as_uint(f4.x); v[cb][c4 * 4 + 1] = __float_as_uint(f4.y);
           v[cb][c4 * 4 + 2] = __float_as_uint(f4.z); v[cb][c4 * 4 + 3] = __float_as_uint(f4.w);
         }
-        issue_store(&tm_out, so, hsel * 64 + cb * 32, tile * 128 + q * 32);
+        if (!p.cls_g) issue_store(&tm_out, so, hsel * 64 + cb * 32, tile * 128 + q * 32);
       }
-      if (p.emit_g) {
+      if (p.cls_g) {
+        // Last layer: the encoder's final LayerNorm (transformer.py:33), the classifier and the
+        // log-softmax (self_attention.py:26-27) and the caller's softmax(...)[...,1] = sigmoid(z1 - z0)
+        // (predictor.py:225,257-258) on the row that is still in registers: h is never written and the
+        // separate classifier pass (512 B/frame re-read) disappears.  This thread holds 64 of the 128
+        // columns, its partner (same lane, other warp of the quarter) the rest.
+        float s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) s1 += __uint_as_float(v[i >> 5][i & 31]);
+        xs[row * 2 + hsel] = s1;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        const float mean = (s1 + xs[row * 2 + (hsel ^ 1)]) * (1.0f / 128.0f);
+        float s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const float d = __uint_as_float(v[i >> 5][i & 31]) - mean;
+          s2 = fmaf(d, d, s2);
+        }
+        xs[256 + row * 2 + hsel] = s2;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        const float rstd = 1.0f / sqrtf((s2 + xs[256 + row * 2 + (hsel ^ 1)]) * (1.0f / 128.0f) + LN_EPS);
+        const float4* gp = reinterpret_cast<const float4*>(p.cls_g + hsel * 64);
+        const float4* bp2 = reinterpret_cast<const float4*>(p.cls_b + hsel * 64);
+        const float4* w0p = reinterpret_cast<const float4*>(p.cls_w + hsel * 64);
+        const float4* w1p = reinterpret_cast<const float4*>(p.cls_w + 128 + hsel * 64);
+        float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float4 g4 = __ldg(gp + c), b4 = __ldg(bp2 + c), u4 = __ldg(w0p + c), w4 = __ldg(w1p + c);
+          const int i0 = c * 4;
+          const float y0 = (__uint_as_float(v[i0 >> 5][i0 & 31]) - mean) * rstd * g4.x + b4.x;
+          const float y1 = (__uint_as_float(v[(i0 + 1) >> 5][(i0 + 1) & 31]) - mean) * rstd * g4.y + b4.y;
+          const float y2 = (__uint_as_float(v[(i0 + 2) >> 5][(i0 + 2) & 31]) - mean) * rstd * g4.z + b4.z;
+          const float y3 = (__uint_as_float(v[(i0 + 3) >> 5][(i0 + 3) & 31]) - mean) * rstd * g4.w + b4.w;
+          z0 += y0 * u4.x + y1 * u4.y + y2 * u4.z + y3 * u4.w;
+          z1 += y0 * w4.x + y1 * w4.y + y2 * w4.z + y3 * w4.w;
+        }
+        // the upper-half thread hands its partial dots over in the lower-half thread's own (now dead)
+        // exchange slots, so the next tile's statistics cannot race with this read
+        if (hsel == 1) { xs[row * 2] = z0; xs[256 + row * 2] = z1; }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        const long grow = (long)tile * 128 + row;
+        if (hsel == 0 && grow < p.M) {
+          const float a0 = z0 + xs[row * 2] + __ldg(p.cls_bias);
+          const float a1 = z1 + xs[256 + row * 2] + __ldg(p.cls_bias + 1);
+          const float mx = fmaxf(a0, a1);
+          const float lse = mx + log1pf(expf(-fabsf(a1 - a0)));        // log_softmax([a0, a1]), stable
+          if (p.logp) *reinterpret_cast<float2*>(p.logp + grow * 2) = make_float2(a0 - lse, a1 - lse);
+          if (p.prob) p.prob[grow] = 1.0f / (1.0f + expf(a0 - a1));     // softmax(logp)[1]
+        }
+      } else if (p.emit_g) {
         // LayerNorm of the new h row for the next layer's Q/K/V GEMM (transformer.py:235-236): this
         // thread holds 64 of the 128 columns, its partner (same lane, other warp of the quarter) the rest
         float s1 = 0.f;
@@ -359,6 +416,9 @@ cudaError_t launch_ffn_tc(const FfnTcArgs& a, int num_sms, cudaStream_t s, std::
   p.M = a.M; p.h = a.h; p.b1 = a.b1; p.b2 = a.b2;
   p.emit_g = a.emit_out ? a.emit_ln_g : nullptr; p.emit_b = a.emit_ln_b;
   p.h_out = a.h; p.emit_out = a.emit_out;
+  p.cls_g = a.cls_ln_g; p.cls_b = a.cls_ln_b; p.cls_w = a.cls_w; p.cls_bias = a.cls_bias;
+  p.prob = a.prob; p.logp = a.logp;
+  if (p.cls_g && (!p.cls_b || !p.cls_w || !p.cls_bias)) return cudaErrorInvalidValue;
   static thread_local int attr_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);

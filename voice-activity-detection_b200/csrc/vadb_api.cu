@@ -208,6 +208,7 @@ int run_encoder(vadb_handle* h, const int32_t* lengths, int Bc, int T, float* pr
   const int M = Bc * T;
   const float* w = h->w32;
   const bool bf = is_bf16_mode(h);
+  static const bool fuse_cls = !(getenv("VADB_FUSE_CLS") && atoi(getenv("VADB_FUSE_CLS")) == 0);
   for (int l = 0; l < h->cfg.num_layers; ++l) {
     const LayerOffsets& lo = h->lay.layers[l];
     int rc;
@@ -244,6 +245,11 @@ int run_encoder(vadb_handle* h, const int32_t* lengths, int Bc, int T, float* pr
         if (l + 1 < h->cfg.num_layers) {
           f.emit_out = h->ws_aln;
           f.emit_ln_g = w + h->lay.layers[l + 1].ln1_g; f.emit_ln_b = w + h->lay.layers[l + 1].ln1_b;
+        } else if (fuse_cls) {
+          // last layer: final LayerNorm + classifier + log-softmax in the FFN epilogue (no classifier pass)
+          f.cls_ln_g = w + h->lay.lnf_g; f.cls_ln_b = w + h->lay.lnf_b;
+          f.cls_w = w + h->lay.wc; f.cls_bias = w + h->lay.bc;
+          f.prob = prob; f.logp = logp;
         }
         std::string err;
         cudaError_t e = launch_ffn_tc(f, h->num_sms, s, &err);
@@ -285,6 +291,7 @@ int run_encoder(vadb_handle* h, const int32_t* lengths, int Bc, int T, float* pr
       if ((rc = gemm(h, g, s))) return rc;
     }
   }
+  if (bf && fuse_cls) return VADB_OK;
   cudaError_t e = launch_classifier(h->ws_h, w + h->lay.lnf_g, w + h->lay.lnf_b, w + h->lay.wc,
                                     w + h->lay.bc, M, prob, logp, s);
   if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("classifier: ") + cudaGetErrorString(e));

@@ -131,6 +131,14 @@ struct FfnTcArgs {
   const float* b1;         // [512]
   const bf16* w2_bf16;     // [128,512]
   const float* b2;         // [128]
+  // last layer only: final LayerNorm + classifier + log-softmax / sigmoid fused into the epilogue
+  // (h is then NOT written back); cls_ln_g == nullptr -> ordinary layer
+  const float* cls_ln_g;
+  const float* cls_ln_b;
+  const float* cls_w;      // [2,128]
+  const float* cls_bias;   // [2]
+  float* prob;             // [M] or nullptr
+  float* logp;             // [M,2] or nullptr
 };
 cudaError_t launch_ffn_tc(const FfnTcArgs& a, int num_sms, cudaStream_t s, std::string* err);
 
