@@ -37,6 +37,7 @@ constexpr uint32_t BLK_BYTES = 128 * 128 * 2;     // [128 x 128] bf16 block = tw
 constexpr uint32_t HALF_BYTES = 128 * 128;        // [128 rows x 64 k] bf16
 constexpr uint32_t STG_BYTES = 32 * 128;          // per-warp staging: 32 rows x 128 B
 constexpr uint32_t IDESC = idesc_bf16(128, 128, 0, 0);
+constexpr uint32_t IDESC_TF32 = idesc_tf32(128, 128);
 
 enum { BAR_WFULL = 0, BAR_AFULL = 1, BAR_AEMPTY = 4, BAR_ACCFULL = 7, BAR_ACCEMPTY = 11, BAR_RFULL = 15, BAR_REMPTY = 16,
        BAR_COUNT = 17 };
@@ -60,6 +61,8 @@ struct GemmTcParams {
   int res_mod;              // > 0: residual row = output row % res_mod (positional-encoding table)
   int res_tma;              // residual tiles arrive by TMA (tm_o2 doubles as their load map) one tile ahead of
                             // the epilogue instead of per-thread row loads whose DRAM latency nothing hides
+  int tf32;                 // A and W are fp32 in global memory, loaded by TMA and multiplied as tf32 (front end):
+                            // K counts 64-float stages (K/128 of them), element coordinates are halved
   int out_f32;              // 1: fp32 output [M, N]; 0: bf16
   int out_split;            // bf16 outputs: columns [j*128, j*128+128) -> out map j when split (q,k,v)
   // fp32 output with N == 128 only: additionally emit LayerNorm(out_row) in bf16 through tm_o1 -- the A
@@ -159,7 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         for (int kc = 0; kc < KC; ++kc)
           for (int hf = 0; hf < 2; ++hf)
             tma_load_2d(smem_base + off_w + (uint32_t)(nb * KC + kc) * BLK_BYTES + hf * HALF_BYTES, &tm_w,
-                        BAR(BAR_WFULL), kc * 128 + hf * 64, nb * 128);
+                        BAR(BAR_WFULL), (kc * 128 + hf * 64) >> p.tf32, nb * 128);
       pdl_wait();
       if (!p.prod) {
         int ac = 0, n = 0;
@@ -170,7 +173,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
             mbar_arrive_expect_tx(BAR(BAR_AFULL + s), BLK_BYTES);
             for (int hf = 0; hf < 2; ++hf)
               tma_load_2d(smem_base + off_a + s * BLK_BYTES + hf * HALF_BYTES, &tm_a, BAR(BAR_AFULL + s),
-                          kc * 128 + hf * 64, tile * 128);
+                          (kc * 128 + hf * 64) >> p.tf32, tile * 128);
           }
           if (p.res_tma) {        // residual rows of this tile (rows past M read as zeros)
             mbar_wait(BAR(BAR_REMPTY), (n & 1) ^ 1, 18);
@@ -201,13 +204,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
           if (elect_one()) {
             const uint32_t a_lo = a_lo0 + (uint32_t)s * (BLK_BYTES >> 4);
             const uint32_t w_lo = w_lo0 + (uint32_t)(nb * KC + kc) * (BLK_BYTES >> 4);
+            if (p.tf32) {
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf)
+              for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                umma_ss_lh(tmem_base + slot * 128, a_lo + hf * (HALF_BYTES >> 4) + kk * 2,
-                           w_lo + hf * (HALF_BYTES >> 4) + kk * 2, DESC_HI_SW128, IDESC,
-                           (kc | hf | kk) != 0 ? 1u : 0u);
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_ss_lh_tf32(tmem_base + slot * 128, a_lo + hf * (HALF_BYTES >> 4) + kk * 2,
+                                  w_lo + hf * (HALF_BYTES >> 4) + kk * 2, DESC_HI_SW128, IDESC_TF32,
+                                  (kc | hf | kk) != 0 ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_ss_lh(tmem_base + slot * 128, a_lo + hf * (HALF_BYTES >> 4) + kk * 2,
+                             w_lo + hf * (HALF_BYTES >> 4) + kk * 2, DESC_HI_SW128, IDESC,
+                             (kc | hf | kk) != 0 ? 1u : 0u);
+            }
             if (nb == NB - 1) umma_commit(BAR(BAR_AEMPTY + s));   // A chunk no longer needed
             if (kc == KC - 1) umma_commit(BAR(BAR_ACCFULL + slot));
           }
@@ -531,8 +544,10 @@ cudaError_t launch_gemm_tc(const GemmTcArgs& a, int num_sms, cudaStream_t s, std
   if (a.ln_g && a.K != 128) return bad("LayerNorm prologue needs K == 128");
   if (a.residual && a.N != 128) return bad("residual needs N == 128");
   if (a.a_rows && (a.K != 128 || a.a_cols <= 0 || a.a_cols > 128 || a.a_cols % 4)) return bad("bad a_cols");
+  if (a.a_f32_tma && (!a.w_f32 || a.a_cols <= 0 || a.a_cols % 4 || a.K != 128 * ((a.a_cols + 63) / 64) || a.ln_g || a.a_rows))
+    return bad("bad tf32 front-end arguments");
   GemmTcParams p = {};
-  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.tf32 = a.a_f32_tma ? 1 : 0;
   p.prod = a.ln_g ? 1 : (a.a_rows ? 2 : 0);
   p.a_src = a.ln_g ? (const void*)a.a_f32 : a.a_rows;
   p.a_cols = a.a_cols; p.a_is_bf16 = a.a_rows_bf16;
@@ -557,10 +572,19 @@ cudaError_t launch_gemm_tc(const GemmTcArgs& a, int num_sms, cudaStream_t s, std
   if (smem > LIMIT) return bad("shared memory budget exceeded");
 
   CUtensorMap tw, ta, to[3];
-  CUresult r = make_tmap_2d(&tw, a.w_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.K, 64, 128);
-  if (r == CUDA_SUCCESS)
-    r = p.prod ? CUDA_SUCCESS
-               : make_tmap_2d(&ta, a.a_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.K, 64, 128);
+  CUresult r;
+  if (p.tf32) {
+    // fp32 operands, boxes of 32 floats (one 128-byte swizzled row chunk); columns >= a_cols read as zeros
+    r = make_tmap_2d(&tw, a.w_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.N, a.a_cols, 32, 128);
+    if (r == CUDA_SUCCESS) r = make_tmap_2d(&ta, a.a_f32_tma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, a.a_cols, 32, 128);
+  } else {
+    r = make_tmap_2d(&tw, a.w_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.K, 64, 128);
+    if (r == CUDA_SUCCESS)
+      // a_cols (front end, bf16 features): the A rows are only a_cols wide; TMA zero-fills up to K
+      r = p.prod ? CUDA_SUCCESS
+                 : make_tmap_2d(&ta, a.a_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M,
+                                (a.a_cols > 0 && !a.a_rows) ? a.a_cols : a.K, 64, 128);
+  }
   if (p.prod) ta = tw;
   const int ocols = p.out_split ? 128 : a.N;
   for (int j = 0; j < 3 && r == CUDA_SUCCESS; ++j) {

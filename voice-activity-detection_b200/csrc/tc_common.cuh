@@ -174,6 +174,24 @@ __device__ __forceinline__ void umma_ss_lh(uint32_t d_tmem, uint32_t a_lo, uint3
       ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::tf32: both operands are fp32 words in shared memory (K-major, 128B swizzle: 32 elements per 128-byte
+// row), of which the tensor core uses the 19 high bits; K = 8 per instruction (32 bytes, the same
+// descriptor advance as 16 bf16).  Used by the front end so that fp32 log-mel rows go from HBM to the MMA by
+// TMA alone, with no conversion pass.
+__device__ __forceinline__ void umma_ss_lh_tf32(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Instruction descriptor for kind::tf32 (tf32 x tf32 -> fp32): a_format = b_format = 2 (TF32), both K-major.
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 rows on the 128 TMEM lanes, K = 16 bf16
 // packed two per 32-bit column -> 8 columns) is read from tensor memory, so it costs no shared-memory
 // bandwidth.  Used for P V with P written by the softmax threads straight into TMEM.

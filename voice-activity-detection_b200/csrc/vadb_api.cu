@@ -305,10 +305,21 @@ int run_encoder(vadb_handle* h, const int32_t* lengths, int Bc, int T, float* pr
 int front_end(vadb_handle* h, const void* x, int x_is_bf16, int M, int pe_T, int win_W, int win_half,
               int win_jump, cudaStream_t s) {
   const int F = h->cfg.feature_size;
+  static const bool tf32_ok = !(getenv("VADB_FRONT_TF32") && atoi(getenv("VADB_FRONT_TF32")) == 0);
   if (is_bf16_mode(h) && F <= D && F % 4 == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0) {
     GemmTcArgs g = {};
     g.M = M; g.N = D; g.K = D; g.w_bf16 = h->win_bf;
-    g.a_rows = x; g.a_cols = F; g.a_rows_bf16 = x_is_bf16;
+    if (tf32_ok && !x_is_bf16 && win_W == 0) {
+      // fp32 features straight from HBM to the tensor cores (TMA, kind::tf32): no conversion pass, and
+      // 10 mantissa bits instead of bf16's 7 on the raw log-mel values
+      g.a_f32_tma = (const float*)x; g.w_f32 = h->w32 + h->lay.w_in; g.a_cols = F;
+      g.K = 128 * ((F + 63) / 64);
+    } else if (tf32_ok && x_is_bf16 && win_W == 0 && F % 8 == 0) {
+      // bf16 features: plain TMA-fed GEMM, the tensor map is F columns wide and TMA zero-fills up to K = 128
+      g.a_bf16 = (const bf16*)x; g.a_cols = F;
+    } else {
+      g.a_rows = x; g.a_cols = F; g.a_rows_bf16 = x_is_bf16;
+    }
     g.win_W = win_W; g.win_half = win_half; g.win_jump = win_jump;
     g.bias = h->w32 + h->lay.b_in; g.residual = h->pe; g.res_mod = pe_T;
     g.out_f32 = 1; g.out[0] = h->ws_h;
@@ -641,7 +652,9 @@ int vadb_predict_probabilities(vadb_handle* h, const float* feat, int L, int hal
       if ((rc = ensure_bytes(h, &h->win_proj, &h->win_proj_bytes, (size_t)L * D * sizeof(float), false))) return rc;
       GemmTcArgs g = {};
       g.M = L; g.N = D; g.K = D; g.w_bf16 = h->win_bf;
-      g.a_rows = feat; g.a_cols = F; g.a_rows_bf16 = 0;
+      static const bool tf32_ok = !(getenv("VADB_FRONT_TF32") && atoi(getenv("VADB_FRONT_TF32")) == 0);
+      if (tf32_ok) { g.a_f32_tma = feat; g.w_f32 = h->w32 + h->lay.w_in; g.a_cols = F; g.K = 128 * ((F + 63) / 64); }
+      else { g.a_rows = feat; g.a_cols = F; g.a_rows_bf16 = 0; }
       g.bias = h->w32 + h->lay.b_in;
       g.out_f32 = 1; g.out[0] = h->win_proj;
       if ((rc = gemm_tc(h, g, s))) return rc;

@@ -102,6 +102,8 @@ struct GemmTcArgs {
   const bf16* w_bf16;      // [N, K]
   const bf16* a_bf16;      // [M, K] (when ln_g == nullptr)
   const float* a_f32;      // [M, 128] fp32 rows through LayerNorm (when ln_g != nullptr)
+  const float* a_f32_tma;  // front end, tf32 mode: [M, a_cols] fp32 rows loaded by TMA and multiplied as tf32 with
+  const float* w_f32;      //   the fp32 weight [N, a_cols]; K must be 128 * ceil(a_cols / 64) (64-float stages)
   const void* a_rows;      // front end: [*, a_cols] fp32/bf16 feature rows, converted + zero-padded to K = 128
   int a_cols, a_rows_bf16;
   int win_W, win_half, win_jump;   // front end: window gather folded into the A-row index (win_W > 0)
