@@ -197,6 +197,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL's own banner ("NCCL version ...", printed when the box
+        # exports NCCL_DEBUG=VERSION/INFO) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
