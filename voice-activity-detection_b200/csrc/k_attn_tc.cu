@@ -41,6 +41,7 @@ constexpr int BKV = 64;          // keys per K/V tile
 constexpr int NK = 3;            // K ring depth (K(j+2) is requested once Q K^T(j-1) retired)
 constexpr int NV = 3;            // V ring depth (V(j) is requested once P V(j-3) retired: three steps of latency cover)
 constexpr int NTHREADS = 352;    // 8 softmax warps + TMA producer + one MMA-issuing warp per query tile
+constexpr int NTHREADS_EPI = 512; // ... + a spare warp (warpgroup alignment) + a 4-warp epilogue warpgroup
 
 constexpr uint32_t Q_HALF_BYTES = BM * 128;          // [128 rows x 64 d] bf16 = 16 KB
 constexpr uint32_t Q_TILE_BYTES = 2 * Q_HALF_BYTES;  // two d-halves
@@ -53,13 +54,18 @@ constexpr uint32_t OFF_K = OFF_Q + 2 * Q_TILE_BYTES;
 constexpr uint32_t OFF_V = OFF_K + NK * KV_TILE_BYTES;
 constexpr uint32_t OFF_OST = OFF_V + NV * KV_TILE_BYTES;        // O staging: [tile][d half] x 16 KB
 constexpr uint32_t OFF_BAR = OFF_OST + 4 * P_TILE_BYTES;
-constexpr uint32_t OFF_SCR = OFF_BAR + 256;        // 256 floats of scratch + one zero word (token pinning)
+constexpr uint32_t OFF_SCR = OFF_BAR + 256;        // [2][128] floats 1/l handed to the epilogue warpgroup, then 64 bytes:
+                                                   // zero word (+0), TMEM base (+4), 8 dummy words (token pinning, +32)
 constexpr uint32_t SMEM_BYTES = OFF_SCR + 1024 + 64;
 constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;   // slack for 1024-byte alignment
 
 // barrier slots (8 bytes each) at OFF_BAR
 enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 5, B_VFULL = 9, B_VEMPTY = 12, B_SFULL = 15 /* [t][buf] */,
-       B_PFULL = 19, B_OFULL = 21, B_QEMPTY = 23, B_COUNT = 24 };
+       B_PFULL = 19, B_OFULL = 21, B_QEMPTY = 23,
+       // epilogue-warpgroup variant: per query tile, "last P V of the item retired", "1/l written",
+       // "1/l consumed" and "O_t read out of TMEM"
+       B_OFINAL = 24, B_LFULL = 26, B_LFREE = 28, B_OFREE = 30, B_COUNT = 32 };
+static_assert(8 * B_COUNT <= 256, "barrier region");
 static_assert(NK <= 4 && NV <= 3, "barrier slots");
 
 constexpr uint32_t TMEM_COLS = 512;
@@ -85,7 +91,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 // named barriers: 1/2 = MUFU token (softmax warpgroup 0 / 1 may run its exponentials), 3+t = warpgroup t
-enum { NB_TOKEN0 = 1, NB_TOKEN1 = 2, NB_WG = 3 };
+enum { NB_TOKEN0 = 1, NB_TOKEN1 = 2, NB_WG = 3 /* +t */, NB_EPI = 5 };
 
 // Work items.  idx < n_full: one clip x 256 query rows (two tiles sharing K/V).  The pairs of the last,
 // partially filled round are split into single-tile items (idx >= n_full) so that the tail of the launch
@@ -112,23 +118,55 @@ __device__ __forceinline__ Item get_item(int idx, int n_full, int npairs, int T,
 // VAR: softmax-schedule variant bits (selected on the host, launch_attn_tc):
 //   bit 0  hand the SFU token to the other warpgroup after element EARLY_IDX of a step instead of after
 //          the last one: its barrier / LDS / first-FFMA start-up latency overlaps our last exponentials
-//   bit 1  store P in two 32-key halves: the tcgen05.st of the first half overlaps the exponentials of
-//          the second
+//   (bit 1, P stored in two 32-key halves, was measured without effect and removed: the rare redo of a
+//          step re-reads the scores from TMEM, which the early half-store would have overwritten)
 //   bits 2-3  fraction of the exponentials evaluated on the FMA pipe (Cody-Waite + degree-3 minimax,
 //          rel. error 7.5e-5, far below the bf16 rounding of P) instead of the SFU: 0, 1/4, 3/8, 1/2
 //   bit 4  no SFU token (the warpgroups run free)
 //   bits 5-6  element index of the early hand-over: 46, 30, 16
-#define VADB_ATTN_VARIANTS(X) X(0) X(1) X(3) X(5) X(33)
+#define VADB_ATTN_VARIANTS(X) X(0) X(1)
 constexpr int ATTN_DEFAULT_VARIANT = 1;
+constexpr bool ATTN_DEFAULT_EPI = false;
 template <int VAR> __device__ __forceinline__ bool use_poly(int i) {
   constexpr int f = (VAR >> 2) & 3;
   return f == 1 ? (i & 3) == 3 : f == 2 ? ((i & 7) == 1 || (i & 7) == 4 || (i & 7) == 7) : f == 3 ? (i & 1) == 1 : false;
 }
 
+// Rare path of a softmax step (the running max grew by more than 2^RESCALE_THRESHOLD): redo the step
+// against the new reference max from the scores that are still in TMEM (P has not been stored yet), eight
+// keys per trip; P chunk c (4 columns) lands on score columns that were read in trips <= c.  Deliberately
+// NOT inlined: a second inlined copy of the unrolled exponential code sat as ~7 KB of cold instructions in
+// the middle of every step (a shared copy with the redo looping back spills ~30 registers: +25 %).
+// Returns the row sum of the new P.
+static __device__ __noinline__ float redo_step_from_tmem(uint32_t tsb, float m_new, float c, int kbase, int len) {
+  float ps = 0.f;
+#pragma unroll 1
+  for (int cch = 0; cch < 8; ++cch) {
+    uint32_t sx[8], px[4];
+    tmem_ld8(tsb + cch * 8, sx);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      const int key = kbase + cch * 8 + i;
+      const float s0 = key < len ? __uint_as_float(sx[i]) : -CUDART_INF_F;
+      const float s1 = key + 1 < len ? __uint_as_float(sx[i + 1]) : -CUDART_INF_F;
+      const float p0 = fast_exp2(fmaf(s0, c, -m_new)), p1 = fast_exp2(fmaf(s1, c, -m_new));
+      ps += p0 + p1;
+      px[i >> 1] = pack_bf16(p0, p1);
+    }
+    tmem_st4(tsb + cch * 4, px);
+  }
+  return ps;
+}
+
 template <int VAR> constexpr int early_idx() { return ((VAR >> 5) & 3) == 0 ? 46 : ((VAR >> 5) & 3) == 1 ? 30 : 16; }
 
-template <bool TRACE, int VAR>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// EPI: the O_t / l -> bf16 -> TMA-store epilogue runs on its own warpgroup (warps 12-15) instead of on the
+// softmax warpgroups, which go straight on to the next work item (their ~1.8 k-cycle epilogue per item was
+// ~10 % of a CTA's time).  168-register softmax warps do not fit a 512-thread CTA (128 per thread), so the
+// register file is re-partitioned with setmaxnreg: softmax warpgroups 168, the two service warpgroups 88.
+template <bool TRACE, int VAR, bool EPI>
+__global__ void __launch_bounds__(EPI ? NTHREADS_EPI : NTHREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
                bf16* __restrict__ O, const int32_t* __restrict__ lengths, int T, int npairs, int n_items,
@@ -138,7 +176,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   unsigned char* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar0 = smem_base + OFF_BAR;
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_BAR + 8 * B_COUNT);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_SCR + 1024 + 4);
+  volatile float* linv = reinterpret_cast<volatile float*>(smem_gen + OFF_SCR);          // [2][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -157,6 +196,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     for (int t = 0; t < 2; ++t) {
       mbar_init(BAR(B_PFULL + t), 4);          // one arrival per softmax warp
       mbar_init(BAR(B_OFULL + t), 1);
+      mbar_init(BAR(B_OFINAL + t), 1);
+      mbar_init(BAR(B_LFULL + t), 4);          // one arrival per softmax warp
+      mbar_init(BAR(B_LFREE + t), 4);          // one arrival per epilogue warp
+      mbar_init(BAR(B_OFREE + t), 4);
     }
     mbar_fence_init();
     *reinterpret_cast<volatile float*>(smem_gen + OFF_SCR + 1024) = 0.f;
@@ -175,7 +218,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   if (threadIdx.x == 0) pdl_launch_dependents();
   pdl_wait();                 // the set-up above overlaps the previous kernel's tail (vadb_common.cuh)
 
-  if (warp == 8) {
+  // Role dispatch by warpgroup, so that in the EPI variant every warpgroup executes exactly one setmaxnreg
+  // (2 x 128 x 168 + 2 x 128 x 88 = 65536 registers) at the top of its own branch.
+  if (warp >= 8 && warp < 12) {
+   if (EPI) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+   if (warp == 8) {
     // ======================= TMA producer =======================
     if (lane == 0) {
       int kc = 0, vc = 0, nq = 0;              // K tiles / V tiles / Q loads issued so far
@@ -255,7 +302,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       if (lane < n) mbar_wait(lane == 0 ? b0 : lane == 1 ? b1 : b2, lane == 0 ? p0 : lane == 1 ? p1 : p2, 6);
       __syncwarp();
     };
-    int kc = 0, vc = 0, nq = 0, n_item = 0;
+    int kc = 0, vc = 0, nq = 0, n_item = 0, n_live = 0;
     int g = 0;                                  // softmax steps issued so far for this query tile
     for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n_item) {
       const Item it = get_item(idx, n_full, npairs, T, lengths);
@@ -296,9 +343,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           mbar_wait(BAR(B_PFULL + t), (g + j) & 1, 8);
           tc_fence_after();
           TR(64 + j * 16 + t * 4 + 1);
+          // epilogue-warpgroup variant: the first P V of an item overwrites O_t, which the epilogue
+          // warpgroup must have read out (n_live counts the items in which this tile was live)
+          if (EPI && j == 0) mbar_wait(BAR(B_OFREE + t), (n_live & 1) ^ 1, 15);
           if (elect_one()) {
             issue_pv(vs, (g + j) & 1, j > 0 ? 1u : 0u);
             umma_commit(BAR(B_OFULL + t));
+            if (EPI && j == nkv - 1) umma_commit(BAR(B_OFINAL + t));
             umma_commit(BAR(B_VEMPTY + vs));
             if (more) {
               issue_qk(kn, (g + j) & 1);
@@ -322,20 +373,83 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         TR(64 + j * 16 + t * 4 + 3);
       }
       kc += nkv; vc += nkv;
-      if (live) g += nkv;
+      if (live) { g += nkv; ++n_live; }
     }
-  } else {
+   }
+  } else if (EPI && warp >= 12) {
+    // ======================= epilogue warpgroup (EPI variant) =======================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    // O_t / l -> bf16 -> two 128B-swizzled staging tiles (64 columns each) -> TMA stores in full lines; rows
+    // past T are clipped by the tensor map.  One thread per query row (TMEM lane), both tiles in turn.
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const bool leader = threadIdx.x == 12 * 32;
+    int n_live[2] = {0, 0}, n_item = 0;
+    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n_item) {
+      const Item it = get_item(idx, n_full, npairs, T, lengths);
+      if (!it.valid || it.nkv == 0) continue;
+      for (int t = 0; t < it.ntile; ++t) {
+        const uint32_t to = tmem_base + lane_addr + TM_O + 128 * t;
+        unsigned char* ost = smem_gen + OFF_OST + t * 2 * P_TILE_BYTES;
+        mbar_wait(BAR(B_LFULL + t), n_live[t] & 1, 17);
+        const float inv = linv[t * BM + row];
+        mbar_wait(BAR(B_OFINAL + t), n_live[t] & 1, 18);
+        tc_fence_after();
+        // the staging tiles of this query tile were handed to the TMA engine one whole item ago
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        nbar_sync(NB_EPI, 128);
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t ov[2][32];
+          tmem_ld32(to + hf * 64, ov[0]);
+          tmem_ld32(to + hf * 64 + 32, ov[1]);
+          tmem_ld_wait();
+          if (hf == 1) {
+            // O_t and 1/l are in registers: the next item may overwrite them
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(BAR(B_OFREE + t)); mbar_arrive(BAR(B_LFREE + t)); }
+          }
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            uint4 o4;
+            const uint32_t* src = &ov[ch >> 2][(ch & 3) * 8];
+            o4.x = pack_bf16_alu(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+            o4.y = pack_bf16_alu(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+            o4.z = pack_bf16_alu(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+            o4.w = pack_bf16_alu(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+            *reinterpret_cast<uint4*>(ost + hf * P_TILE_BYTES + sw128_offset(row, ch)) = o4;
+          }
+        }
+        fence_proxy_async_smem();
+        nbar_sync(NB_EPI, 128);
+        if (leader) {
+          const uint32_t src = smem_base + OFF_OST + t * 2 * P_TILE_BYTES;
+          tma_store_3d(&tm_o, src, 0, it.q0 + t * BM, it.b);
+          tma_store_3d(&tm_o, src + P_TILE_BYTES, 64, it.q0 + t * BM, it.b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++n_live[t];
+      }
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else if (warp < 8) {
     // ======================= softmax warpgroups =======================
+    if (EPI) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    // barrier waits of this (raised-budget) region use their own slow path: see mbar_wait_hi
+    auto swait = [&](uint32_t bar, uint32_t parity, int tag) {
+      if (EPI) mbar_wait_hi(bar, parity); else mbar_wait(bar, parity, tag);
+    };
     const int t = warp >> 2;                       // query tile of this warpgroup
     const int row = (warp & 3) * 32 + lane;        // row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t ts = tmem_base + lane_addr + TM_S + 128 * t;
     const uint32_t to = tmem_base + lane_addr + TM_O + 128 * t;
     unsigned char* ost = smem_gen + OFF_OST + t * 2 * P_TILE_BYTES;
-    volatile float* scratch = reinterpret_cast<volatile float*>(smem_gen + OFF_SCR);
+    volatile float* scratch = reinterpret_cast<volatile float*>(smem_gen + OFF_SCR + 1024);   // [0] = 0.f, [8..15] dummies
     // softmax in the exp2 domain: p = 2^(s*c - m), c = log2(e)/sqrt(d_head)  (transformer.py:362)
     const float c = 1.4426950408889634f * 0.08838834764831845f;
-    int g = 0, n_item = 0;                         // softmax steps done so far by this warpgroup
+    int g = 0, n_item = 0, n_live = 0;             // softmax steps done so far by this warpgroup
     // The two warpgroups take turns on the SFU: exp2 throughput (16/clk/SM) is the scarce resource of
     // this kernel, so their exponential phases are serialised with a token and everything else
     // (TMEM traffic, row max, barrier traffic) of one overlaps the exponentials of the other.
@@ -376,7 +490,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           // non-blocking probe, consumed after the exponentials: "P V of the previous step retired"
           o_ready = (j == 0) || mbar_test_wait(BAR(B_OFULL + t), (g - 1) & 1);
           const int kbase = j * BKV;
-          if (kbase + BKV > len) {                     // warp-uniform: only the last tile holds masked keys
+          if (kbase + BKV > len) {           // warp-uniform: only the last tile holds masked keys
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2)
 #pragma unroll
@@ -394,17 +508,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
               const float s0 = __uint_as_float(sv[i >> 5][i & 31]), s1 = __uint_as_float(sv[(i + 1) >> 5][(i + 1) & 31]);
               const float a0 = fmaf(s0, c, -m_use);
               const float a1 = fmaf(s1, c, -m_use);
-              const float p0 = use_poly<VAR>(i) ? poly_exp2(a0) : pinned ? fast_exp2_pinned(a0) : fast_exp2(a0);
-              const float p1 = use_poly<VAR>(i + 1) ? poly_exp2(a1) : pinned ? fast_exp2_pinned(a1) : fast_exp2(a1);
+              const float p0 = use_poly<VAR>(i) ? poly_exp2(a0) : fast_exp2_pinned(a0);
+              const float p1 = use_poly<VAR>(i + 1) ? poly_exp2(a1) : fast_exp2_pinned(a1);
               ps4[(i >> 1) & 3] += p0 + p1;
               mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(s0, s1));
               pk[i >> 1] = pack_bf16(p0, p1);
               if (i == 62) p_last = p1;
               if ((VAR & 1) && pinned && i == early_idx<VAR>() && pingpong) {
-                scratch[threadIdx.x] = p0;
+                scratch[8 + (threadIdx.x & 7)] = p0;
                 nbar_arrive(t == 0 ? NB_TOKEN1 : NB_TOKEN0, 256);
               }
-              if ((VAR & 2) && i == 30) tmem_st16p(tsb, pk);       // keys 0..31 of P_t
             }
             psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
             mxl = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * c;
@@ -426,28 +539,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             nbar_sync(t == 0 ? NB_TOKEN0 : NB_TOKEN1, 256);
             // data dependence on a load issued after the barrier: keeps ptxas from hoisting the
             // exponentials above the token wait
-            m_use += scratch[256];
+            m_use += scratch[0];
           }
           TS(2);
+          float alpha = 1.f;
           exps(m_use, true);
           if (pingpong && !(VAR & 1)) {
             // ... and the token is handed over once the last exponential has been through the SFU
-            scratch[threadIdx.x] = p_last;
+            scratch[8 + (threadIdx.x & 7)] = p_last;
             nbar_arrive(t == 0 ? NB_TOKEN1 : NB_TOKEN0, 256);
           }
-          TS(3);
-          float alpha = 1.f;
           rescale = (j > 0) && __any_sync(0xffffffffu, mxl > m_ref + RESCALE_THRESHOLD);
           if (rescale) {                               // warp-uniform, rare
+            // redo against the new reference max, out of line (see redo_step_from_tmem)
             const float m_new = fmaxf(m_ref, mxl);
             alpha = fast_exp2(m_ref - m_new);
             m_ref = m_new;
-            exps(m_ref, false);
+            psum = redo_step_from_tmem(tsb, m_new, c, j * BKV, len);
           }
+          TS(3);
           l_sum = l_sum * alpha + psum;
           // previous P V must have retired before O is rescaled (P itself lives in this step's S buffer)
           if (rescale) {
-            if (!o_ready) mbar_wait(BAR(B_OFULL + t), (g - 1) & 1, 10);
+            if (!o_ready) swait(BAR(B_OFULL + t), (g - 1) & 1, 10);
             tc_fence_after();
 #pragma unroll 1
             for (int cb = 0; cb < 4; ++cb) {
@@ -459,8 +573,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
               tmem_st32(to + cb * 32, ov);
             }
           }
-          if (VAR & 2) tmem_st16p(tsb + 16, pk + 16);  // keys 32..63 (the first half went out mid-step)
-          else tmem_st32(tsb, pk);                     // P_t (bf16 pairs) over the head of S_t[buf]
+          if (!rescale) tmem_st32(tsb, pk);            // P_t (bf16 pairs) over the head of S_t[buf]
           TS(4);
         }
         // scores of the next step: TMEM -> registers.  If they are already there the load is issued now and
@@ -480,7 +593,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           // An mbarrier may run at most one phase ahead of its waiter: do not signal P_t(j) before the
           // MMA warp has consumed P_t(j-1) (it has once P V(j-1) retired).  The probe was issued at the
           // top of the step, so this is normally free.
-          if (!o_ready && !rescale) mbar_wait(BAR(B_OFULL + t), (g - 1) & 1, 12);
+          if (!o_ready && !rescale) swait(BAR(B_OFULL + t), (g - 1) & 1, 12);
           tmem_st_wait();
           TS(6);
           tc_fence_before();
@@ -489,7 +602,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           ++g;
         }
         if (has_next && !s_loaded) {
-          mbar_wait(BAR(B_SFULL + 2 * t + (gn & 1)), (gn >> 1) & 1, 9);
+          swait(BAR(B_SFULL + 2 * t + (gn & 1)), (gn >> 1) & 1, 9);
           tc_fence_after();
           tmem_ld32(tsn, sv[0]);
           tmem_ld32(tsn + 32, sv[1]);
@@ -498,11 +611,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         if (work) TS(7);
       }
 
+      if (EPI) {
+        // hand the row sums to the epilogue warpgroup and go straight on to the next item
+        swait(BAR(B_LFREE + t), (n_live & 1) ^ 1, 16);      // previous item's 1/l consumed
+        linv[t * BM + row] = 1.0f / l_sum;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_LFULL + t));
+        ++n_live;
+        continue;
+      }
       // epilogue: O_t / l -> bf16 -> two 128B-swizzled staging tiles (64 columns each) -> TMA stores in
       // full lines; rows past T are clipped by the tensor map.  The next item's first P V (which
       // overwrites O_t) is ordered behind these TMEM reads by this warp's own next p_full arrival.
       if (TRACE && (threadIdx.x & 127) == 0) TR(32 + t * 4 + 0);
-      mbar_wait(BAR(B_OFULL + t), (g - 1) & 1, 11);
+      swait(BAR(B_OFULL + t), (g - 1) & 1, 11);
       tc_fence_after();
       if (TRACE && (threadIdx.x & 127) == 0) TR(32 + t * 4 + 1);
       const float inv = 1.0f / l_sum;
@@ -627,7 +749,8 @@ cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o,
   }
   static const bool want_trace = getenv("VADB_ATTN_TRACE") != nullptr;
   static const int variant = getenv("VADB_ATTN_VARIANT") ? atoi(getenv("VADB_ATTN_VARIANT")) : ATTN_DEFAULT_VARIANT;
-  auto run = [&](auto kern_trace, auto kern) -> cudaError_t {
+  static const bool use_epi = getenv("VADB_ATTN_EPI") ? atoi(getenv("VADB_ATTN_EPI")) != 0 : ATTN_DEFAULT_EPI;
+  auto run = [&](auto kern_trace, auto kern, auto kern_epi) -> cudaError_t {
     if (want_trace) {
       cudaError_t e = cudaFuncSetAttribute(kern_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
       if (e != cudaSuccess) return e;
@@ -666,13 +789,19 @@ cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o,
       return cudaGetLastError();
     }
     // the attribute is per function and per device; setting it on every launch costs ~1 us of host time
+    if (use_epi) {
+      cudaError_t e = cudaFuncSetAttribute(kern_epi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
+      if (e != cudaSuccess) return e;
+      return launch_k(kern_epi, (unsigned)grid, NTHREADS_EPI, SMEM_ALLOC, s, tq, tk, tv, to, o, lengths, T, npairs, n_items,
+                      n_full, (long long*)nullptr);
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
     if (e != cudaSuccess) return e;
     return launch_k(kern, (unsigned)grid, NTHREADS, SMEM_ALLOC, s, tq, tk, tv, to, o, lengths, T, npairs, n_items, n_full,
                     (long long*)nullptr);
   };
   switch (variant) {
-#define VADB_ATTN_CASE(V) case V: return run(attn_tc_kernel<true, V>, attn_tc_kernel<false, V>);
+#define VADB_ATTN_CASE(V) case V: return run(attn_tc_kernel<true, V, false>, attn_tc_kernel<false, V, false>, attn_tc_kernel<false, V, true>);
     VADB_ATTN_VARIANTS(VADB_ATTN_CASE)
 #undef VADB_ATTN_CASE
     default:

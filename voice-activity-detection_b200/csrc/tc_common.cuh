@@ -53,8 +53,9 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
-  if (mbar_try_wait(bar, parity)) return;
+// The slow path (clock reads, report, trap) is kept out of line so that the hot loops that wait on
+// barriers stay compact in the instruction cache.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int tag) {
   const long long t0 = clock64();
   bool reported = false;
   while (!mbar_try_wait(bar, parity)) {
@@ -66,6 +67,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
     }
     if (dt > 5000000000LL) __trap();        // ... then fail the launch instead of hanging the GPU
   }
+}
+// Variant for code that runs under a raised setmaxnreg budget: ptxas compiles a kernel to the LOWEST
+// budget of all regions that share a callee (measured: a noinline function called from both an 88- and
+// a 168-register region caps the whole kernel at 88), so such regions get their own copy of the slow
+// path, without the printf (vprintf would be shared again).
+static __device__ __noinline__ void mbar_wait_slow_hi(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > 5000000000LL) __trap();
+}
+__device__ __forceinline__ void mbar_wait_hi(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow_hi(bar, parity);
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;   // a second bounded hardware wait before leaving the hot path
+  mbar_wait_slow(bar, parity, tag);
 }
 
 // ------------------------------------------------------------------ proxy / tcgen05 fences
@@ -240,6 +260,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
