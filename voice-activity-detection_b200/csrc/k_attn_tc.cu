@@ -41,7 +41,6 @@ constexpr int BKV = 64;          // keys per K/V tile
 constexpr int NK = 3;            // K ring depth (K(j+2) is requested once Q K^T(j-1) retired)
 constexpr int NV = 3;            // V ring depth (V(j) is requested once P V(j-3) retired: three steps of latency cover)
 constexpr int NTHREADS = 352;    // 8 softmax warps + TMA producer + one MMA-issuing warp per query tile
-constexpr int NTHREADS_EPI = 512; // ... + a spare warp (warpgroup alignment) + a 4-warp epilogue warpgroup
 
 constexpr uint32_t Q_HALF_BYTES = BM * 128;          // [128 rows x 64 d] bf16 = 16 KB
 constexpr uint32_t Q_TILE_BYTES = 2 * Q_HALF_BYTES;  // two d-halves
@@ -54,17 +53,14 @@ constexpr uint32_t OFF_K = OFF_Q + 2 * Q_TILE_BYTES;
 constexpr uint32_t OFF_V = OFF_K + NK * KV_TILE_BYTES;
 constexpr uint32_t OFF_OST = OFF_V + NV * KV_TILE_BYTES;        // O staging: [tile][d half] x 16 KB
 constexpr uint32_t OFF_BAR = OFF_OST + 4 * P_TILE_BYTES;
-constexpr uint32_t OFF_SCR = OFF_BAR + 256;        // [2][128] floats 1/l handed to the epilogue warpgroup, then 64 bytes:
-                                                   // zero word (+0), TMEM base (+4), 8 dummy words (token pinning, +32)
+constexpr uint32_t OFF_SCR = OFF_BAR + 256;        // 1 KB unused, then 64 bytes: zero word (+0), TMEM base (+4),
+                                                   // 8 dummy words (token pinning, +32)
 constexpr uint32_t SMEM_BYTES = OFF_SCR + 1024 + 64;
 constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;   // slack for 1024-byte alignment
 
 // barrier slots (8 bytes each) at OFF_BAR
 enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 5, B_VFULL = 9, B_VEMPTY = 12, B_SFULL = 15 /* [t][buf] */,
-       B_PFULL = 19, B_OFULL = 21, B_QEMPTY = 23,
-       // epilogue-warpgroup variant: per query tile, "last P V of the item retired", "1/l written",
-       // "1/l consumed" and "O_t read out of TMEM"
-       B_OFINAL = 24, B_LFULL = 26, B_LFREE = 28, B_OFREE = 30, B_COUNT = 32 };
+       B_PFULL = 19, B_OFULL = 21, B_QEMPTY = 23, B_COUNT = 24 };
 static_assert(8 * B_COUNT <= 256, "barrier region");
 static_assert(NK <= 4 && NV <= 3, "barrier slots");
 
@@ -91,7 +87,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 // named barriers: 1/2 = MUFU token (softmax warpgroup 0 / 1 may run its exponentials), 3+t = warpgroup t
-enum { NB_TOKEN0 = 1, NB_TOKEN1 = 2, NB_WG = 3 /* +t */, NB_EPI = 5 };
+enum { NB_TOKEN0 = 1, NB_TOKEN1 = 2, NB_WG = 3 /* +t */ };
 
 // Work items.  idx < n_full: one clip x 256 query rows (two tiles sharing K/V).  The pairs of the last,
 // partially filled round are split into single-tile items (idx >= n_full) so that the tail of the launch
@@ -126,11 +122,30 @@ __device__ __forceinline__ Item get_item(int idx, int n_full, int npairs, int T,
 //   bits 5-6  element index of the early hand-over: 46, 30, 16
 #define VADB_ATTN_VARIANTS(X) X(0) X(1)
 constexpr int ATTN_DEFAULT_VARIANT = 1;
-constexpr bool ATTN_DEFAULT_EPI = false;
+constexpr int ATTN_DEFAULT_STAGGER = 1;
 template <int VAR> __device__ __forceinline__ bool use_poly(int i) {
   constexpr int f = (VAR >> 2) & 3;
   return f == 1 ? (i & 3) == 3 : f == 2 ? ((i & 7) == 1 || (i & 7) == 4 || (i & 7) == 7) : f == 3 ? (i & 1) == 1 : false;
 }
+
+// Order in which a CTA walks its work items.  Every CTA has the same amount of work per item, so with the
+// plain order (round r -> item blockIdx + r * grid) all 148 CTAs reach their item boundaries together and
+// their Q/K/V requests for the next item (96 KB each) arrive as one 14 MB burst.  When the last round
+// consists of the shorter single-tile items, odd CTAs run theirs FIRST: odd and even CTAs are then offset
+// by the difference between a single-tile and a two-tile item for the rest of the launch.
+struct ItemWalk {
+  int first, n, rot;    // first item index, number of items of this CTA, 1 -> the last item goes first
+  __device__ __forceinline__ ItemWalk(int n_items, int n_full, int stagger) {
+    first = blockIdx.x;
+    n = first < n_items ? (n_items - first + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int last = first + (n - 1) * (int)gridDim.x;
+    rot = (stagger && n > 1 && (blockIdx.x & 1) && last >= n_full) ? 1 : 0;
+  }
+  __device__ __forceinline__ int idx(int r) const {
+    const int rr = rot ? (r == 0 ? n - 1 : r - 1) : r;
+    return first + rr * (int)gridDim.x;
+  }
+};
 
 // Rare path of a softmax step (the running max grew by more than 2^RESCALE_THRESHOLD): redo the step
 // against the new reference max from the scores that are still in TMEM (P has not been stored yet), eight
@@ -161,23 +176,18 @@ static __device__ __noinline__ float redo_step_from_tmem(uint32_t tsb, float m_n
 
 template <int VAR> constexpr int early_idx() { return ((VAR >> 5) & 3) == 0 ? 46 : ((VAR >> 5) & 3) == 1 ? 30 : 16; }
 
-// EPI: the O_t / l -> bf16 -> TMA-store epilogue runs on its own warpgroup (warps 12-15) instead of on the
-// softmax warpgroups, which go straight on to the next work item (their ~1.8 k-cycle epilogue per item was
-// ~10 % of a CTA's time).  168-register softmax warps do not fit a 512-thread CTA (128 per thread), so the
-// register file is re-partitioned with setmaxnreg: softmax warpgroups 168, the two service warpgroups 88.
-template <bool TRACE, int VAR, bool EPI>
-__global__ void __launch_bounds__(EPI ? NTHREADS_EPI : NTHREADS, 1)
+template <bool TRACE, int VAR>
+__global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
                bf16* __restrict__ O, const int32_t* __restrict__ lengths, int T, int npairs, int n_items,
-               int n_full, long long* trace) {
+               int n_full, int stagger, long long* trace) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar0 = smem_base + OFF_BAR;
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_SCR + 1024 + 4);
-  volatile float* linv = reinterpret_cast<volatile float*>(smem_gen + OFF_SCR);          // [2][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -196,10 +206,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     for (int t = 0; t < 2; ++t) {
       mbar_init(BAR(B_PFULL + t), 4);          // one arrival per softmax warp
       mbar_init(BAR(B_OFULL + t), 1);
-      mbar_init(BAR(B_OFINAL + t), 1);
-      mbar_init(BAR(B_LFULL + t), 4);          // one arrival per softmax warp
-      mbar_init(BAR(B_LFREE + t), 4);          // one arrival per epilogue warp
-      mbar_init(BAR(B_OFREE + t), 4);
     }
     mbar_fence_init();
     *reinterpret_cast<volatile float*>(smem_gen + OFF_SCR + 1024) = 0.f;
@@ -218,15 +224,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   if (threadIdx.x == 0) pdl_launch_dependents();
   pdl_wait();                 // the set-up above overlaps the previous kernel's tail (vadb_common.cuh)
 
-  // Role dispatch by warpgroup, so that in the EPI variant every warpgroup executes exactly one setmaxnreg
-  // (2 x 128 x 168 + 2 x 128 x 88 = 65536 registers) at the top of its own branch.
-  if (warp >= 8 && warp < 12) {
-   if (EPI) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-   if (warp == 8) {
+  if (warp == 8) {
     // ======================= TMA producer =======================
     if (lane == 0) {
       int kc = 0, vc = 0, nq = 0;              // K tiles / V tiles / Q loads issued so far
-      for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
+      const ItemWalk walk(n_items, n_full, stagger);
+      for (int r = 0; r < walk.n; ++r) {
+        const int idx = walk.idx(r);
         const Item it = get_item(idx, n_full, npairs, T, lengths);
         if (!it.valid || it.nkv == 0) continue;
         mbar_wait(BAR(B_QEMPTY), (nq & 1) ^ 1, 1);            // every Q K^T of the previous item retired
@@ -302,9 +306,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       if (lane < n) mbar_wait(lane == 0 ? b0 : lane == 1 ? b1 : b2, lane == 0 ? p0 : lane == 1 ? p1 : p2, 6);
       __syncwarp();
     };
-    int kc = 0, vc = 0, nq = 0, n_item = 0, n_live = 0;
+    int kc = 0, vc = 0, nq = 0, n_item = 0;
     int g = 0;                                  // softmax steps issued so far for this query tile
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n_item) {
+    const ItemWalk walk(n_items, n_full, stagger);
+    for (int r = 0; r < walk.n; ++r, ++n_item) {
+      const int idx = walk.idx(r);
       const Item it = get_item(idx, n_full, npairs, T, lengths);
       if (!it.valid || it.nkv == 0) continue;
       const int nkv = it.nkv;
@@ -343,13 +349,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           mbar_wait(BAR(B_PFULL + t), (g + j) & 1, 8);
           tc_fence_after();
           TR(64 + j * 16 + t * 4 + 1);
-          // epilogue-warpgroup variant: the first P V of an item overwrites O_t, which the epilogue
-          // warpgroup must have read out (n_live counts the items in which this tile was live)
-          if (EPI && j == 0) mbar_wait(BAR(B_OFREE + t), (n_live & 1) ^ 1, 15);
           if (elect_one()) {
             issue_pv(vs, (g + j) & 1, j > 0 ? 1u : 0u);
             umma_commit(BAR(B_OFULL + t));
-            if (EPI && j == nkv - 1) umma_commit(BAR(B_OFINAL + t));
             umma_commit(BAR(B_VEMPTY + vs));
             if (more) {
               issue_qk(kn, (g + j) & 1);
@@ -373,73 +375,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         TR(64 + j * 16 + t * 4 + 3);
       }
       kc += nkv; vc += nkv;
-      if (live) { g += nkv; ++n_live; }
+      if (live) g += nkv;
     }
-   }
-  } else if (EPI && warp >= 12) {
-    // ======================= epilogue warpgroup (EPI variant) =======================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-    // O_t / l -> bf16 -> two 128B-swizzled staging tiles (64 columns each) -> TMA stores in full lines; rows
-    // past T are clipped by the tensor map.  One thread per query row (TMEM lane), both tiles in turn.
-    const int row = (warp & 3) * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    const bool leader = threadIdx.x == 12 * 32;
-    int n_live[2] = {0, 0}, n_item = 0;
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n_item) {
-      const Item it = get_item(idx, n_full, npairs, T, lengths);
-      if (!it.valid || it.nkv == 0) continue;
-      for (int t = 0; t < it.ntile; ++t) {
-        const uint32_t to = tmem_base + lane_addr + TM_O + 128 * t;
-        unsigned char* ost = smem_gen + OFF_OST + t * 2 * P_TILE_BYTES;
-        mbar_wait(BAR(B_LFULL + t), n_live[t] & 1, 17);
-        const float inv = linv[t * BM + row];
-        mbar_wait(BAR(B_OFINAL + t), n_live[t] & 1, 18);
-        tc_fence_after();
-        // the staging tiles of this query tile were handed to the TMA engine one whole item ago
-        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        nbar_sync(NB_EPI, 128);
-#pragma unroll 1
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t ov[2][32];
-          tmem_ld32(to + hf * 64, ov[0]);
-          tmem_ld32(to + hf * 64 + 32, ov[1]);
-          tmem_ld_wait();
-          if (hf == 1) {
-            // O_t and 1/l are in registers: the next item may overwrite them
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(BAR(B_OFREE + t)); mbar_arrive(BAR(B_LFREE + t)); }
-          }
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            uint4 o4;
-            const uint32_t* src = &ov[ch >> 2][(ch & 3) * 8];
-            o4.x = pack_bf16_alu(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
-            o4.y = pack_bf16_alu(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
-            o4.z = pack_bf16_alu(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
-            o4.w = pack_bf16_alu(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
-            *reinterpret_cast<uint4*>(ost + hf * P_TILE_BYTES + sw128_offset(row, ch)) = o4;
-          }
-        }
-        fence_proxy_async_smem();
-        nbar_sync(NB_EPI, 128);
-        if (leader) {
-          const uint32_t src = smem_base + OFF_OST + t * 2 * P_TILE_BYTES;
-          tma_store_3d(&tm_o, src, 0, it.q0 + t * BM, it.b);
-          tma_store_3d(&tm_o, src + P_TILE_BYTES, 64, it.q0 + t * BM, it.b);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-        ++n_live[t];
-      }
-    }
-    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  } else if (warp < 8) {
+  } else {
     // ======================= softmax warpgroups =======================
-    if (EPI) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
-    // barrier waits of this (raised-budget) region use their own slow path: see mbar_wait_hi
-    auto swait = [&](uint32_t bar, uint32_t parity, int tag) {
-      if (EPI) mbar_wait_hi(bar, parity); else mbar_wait(bar, parity, tag);
-    };
     const int t = warp >> 2;                       // query tile of this warpgroup
     const int row = (warp & 3) * 32 + lane;        // row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
@@ -449,14 +388,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     volatile float* scratch = reinterpret_cast<volatile float*>(smem_gen + OFF_SCR + 1024);   // [0] = 0.f, [8..15] dummies
     // softmax in the exp2 domain: p = 2^(s*c - m), c = log2(e)/sqrt(d_head)  (transformer.py:362)
     const float c = 1.4426950408889634f * 0.08838834764831845f;
-    int g = 0, n_item = 0, n_live = 0;             // softmax steps done so far by this warpgroup
+    int g = 0, n_item = 0;                         // softmax steps done so far by this warpgroup
     // The two warpgroups take turns on the SFU: exp2 throughput (16/clk/SM) is the scarce resource of
     // this kernel, so their exponential phases are serialised with a token and everything else
     // (TMEM traffic, row max, barrier traffic) of one overlaps the exponentials of the other.
     if (t == 1) nbar_arrive(NB_TOKEN0, 256);       // warpgroup 0 goes first
 
 #define TS(k) do { if (TRACE && (threadIdx.x & 127) == 0) TR(512 + j * 32 + t * 16 + (k)); } while (0)
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n_item) {
+    const ItemWalk walk(n_items, n_full, stagger);
+    for (int r = 0; r < walk.n; ++r, ++n_item) {
+      const int idx = walk.idx(r);
       const Item it = get_item(idx, n_full, npairs, T, lengths);
       const int nkv = it.nkv, len = it.len;
       if (!it.valid) continue;
@@ -561,7 +502,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           l_sum = l_sum * alpha + psum;
           // previous P V must have retired before O is rescaled (P itself lives in this step's S buffer)
           if (rescale) {
-            if (!o_ready) swait(BAR(B_OFULL + t), (g - 1) & 1, 10);
+            if (!o_ready) mbar_wait(BAR(B_OFULL + t), (g - 1) & 1, 10);
             tc_fence_after();
 #pragma unroll 1
             for (int cb = 0; cb < 4; ++cb) {
@@ -593,7 +534,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           // An mbarrier may run at most one phase ahead of its waiter: do not signal P_t(j) before the
           // MMA warp has consumed P_t(j-1) (it has once P V(j-1) retired).  The probe was issued at the
           // top of the step, so this is normally free.
-          if (!o_ready && !rescale) swait(BAR(B_OFULL + t), (g - 1) & 1, 12);
+          if (!o_ready && !rescale) mbar_wait(BAR(B_OFULL + t), (g - 1) & 1, 12);
           tmem_st_wait();
           TS(6);
           tc_fence_before();
@@ -602,7 +543,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           ++g;
         }
         if (has_next && !s_loaded) {
-          swait(BAR(B_SFULL + 2 * t + (gn & 1)), (gn >> 1) & 1, 9);
+          mbar_wait(BAR(B_SFULL + 2 * t + (gn & 1)), (gn >> 1) & 1, 9);
           tc_fence_after();
           tmem_ld32(tsn, sv[0]);
           tmem_ld32(tsn + 32, sv[1]);
@@ -611,20 +552,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         if (work) TS(7);
       }
 
-      if (EPI) {
-        // hand the row sums to the epilogue warpgroup and go straight on to the next item
-        swait(BAR(B_LFREE + t), (n_live & 1) ^ 1, 16);      // previous item's 1/l consumed
-        linv[t * BM + row] = 1.0f / l_sum;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_LFULL + t));
-        ++n_live;
-        continue;
-      }
       // epilogue: O_t / l -> bf16 -> two 128B-swizzled staging tiles (64 columns each) -> TMA stores in
       // full lines; rows past T are clipped by the tensor map.  The next item's first P V (which
       // overwrites O_t) is ordered behind these TMEM reads by this warp's own next p_full arrival.
       if (TRACE && (threadIdx.x & 127) == 0) TR(32 + t * 4 + 0);
-      swait(BAR(B_OFULL + t), (g - 1) & 1, 11);
+      mbar_wait(BAR(B_OFULL + t), (g - 1) & 1, 11);
       tc_fence_after();
       if (TRACE && (threadIdx.x & 127) == 0) TR(32 + t * 4 + 1);
       const float inv = 1.0f / l_sum;
@@ -747,10 +679,10 @@ cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o,
     const int rem = n_pairs % (int)grid;        // pairs in the last, partially filled round
     if (n_pairs > grid && rem > 0 && 2 * rem <= grid) { n_full = n_pairs - rem; n_items = n_full + 2 * rem; }
   }
+  static const int stagger = getenv("VADB_ATTN_STAGGER") ? atoi(getenv("VADB_ATTN_STAGGER")) : ATTN_DEFAULT_STAGGER;
   static const bool want_trace = getenv("VADB_ATTN_TRACE") != nullptr;
   static const int variant = getenv("VADB_ATTN_VARIANT") ? atoi(getenv("VADB_ATTN_VARIANT")) : ATTN_DEFAULT_VARIANT;
-  static const bool use_epi = getenv("VADB_ATTN_EPI") ? atoi(getenv("VADB_ATTN_EPI")) != 0 : ATTN_DEFAULT_EPI;
-  auto run = [&](auto kern_trace, auto kern, auto kern_epi) -> cudaError_t {
+  auto run = [&](auto kern_trace, auto kern) -> cudaError_t {
     if (want_trace) {
       cudaError_t e = cudaFuncSetAttribute(kern_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
       if (e != cudaSuccess) return e;
@@ -758,7 +690,7 @@ cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o,
       const int NTR = 2048;
       cudaMalloc(&dtrace, NTR * sizeof(long long));
       cudaMemsetAsync(dtrace, 0, NTR * sizeof(long long), s);
-      kern_trace<<<(unsigned)grid, NTHREADS, SMEM_ALLOC, s>>>(tq, tk, tv, to, o, lengths, T, npairs, n_items, n_full, dtrace);
+      kern_trace<<<(unsigned)grid, NTHREADS, SMEM_ALLOC, s>>>(tq, tk, tv, to, o, lengths, T, npairs, n_items, n_full, stagger, dtrace);
       std::vector<long long> ht(NTR);
       cudaMemcpyAsync(ht.data(), dtrace, NTR * sizeof(long long), cudaMemcpyDeviceToHost, s);
       cudaStreamSynchronize(s);
@@ -789,19 +721,13 @@ cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o,
       return cudaGetLastError();
     }
     // the attribute is per function and per device; setting it on every launch costs ~1 us of host time
-    if (use_epi) {
-      cudaError_t e = cudaFuncSetAttribute(kern_epi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
-      if (e != cudaSuccess) return e;
-      return launch_k(kern_epi, (unsigned)grid, NTHREADS_EPI, SMEM_ALLOC, s, tq, tk, tv, to, o, lengths, T, npairs, n_items,
-                      n_full, (long long*)nullptr);
-    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
     if (e != cudaSuccess) return e;
     return launch_k(kern, (unsigned)grid, NTHREADS, SMEM_ALLOC, s, tq, tk, tv, to, o, lengths, T, npairs, n_items, n_full,
-                    (long long*)nullptr);
+                    stagger, (long long*)nullptr);
   };
   switch (variant) {
-#define VADB_ATTN_CASE(V) case V: return run(attn_tc_kernel<true, V, false>, attn_tc_kernel<false, V, false>, attn_tc_kernel<false, V, true>);
+#define VADB_ATTN_CASE(V) case V: return run(attn_tc_kernel<true, V>, attn_tc_kernel<false, V>);
     VADB_ATTN_VARIANTS(VADB_ATTN_CASE)
 #undef VADB_ATTN_CASE
     default:

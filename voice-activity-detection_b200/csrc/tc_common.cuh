@@ -68,20 +68,6 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity
     if (dt > 5000000000LL) __trap();        // ... then fail the launch instead of hanging the GPU
   }
 }
-// Variant for code that runs under a raised setmaxnreg budget: ptxas compiles a kernel to the LOWEST
-// budget of all regions that share a callee (measured: a noinline function called from both an 88- and
-// a 168-register region caps the whole kernel at 88), so such regions get their own copy of the slow
-// path, without the printf (vprintf would be shared again).
-static __device__ __noinline__ void mbar_wait_slow_hi(uint32_t bar, uint32_t parity) {
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity))
-    if (clock64() - t0 > 5000000000LL) __trap();
-}
-__device__ __forceinline__ void mbar_wait_hi(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  if (mbar_try_wait(bar, parity)) return;
-  mbar_wait_slow_hi(bar, parity);
-}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   if (mbar_try_wait(bar, parity)) return;   // a second bounded hardware wait before leaving the hot path
