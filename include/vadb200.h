@@ -105,6 +105,33 @@ int vadb_predict_probabilities(vadb_handle* h, const float* feat, int L, int hal
 int vadb_predict_probabilities_host(vadb_handle* h, const float* feat, int L, int half,
                                     int jump, float* probs_LW, float* mean_L);
 
+/* ---- log-mel front end on the device: replaces FeatureExtractor.extract_with_postprocessing
+ *      (vad/acoustics/feature_extractor.py:71-80) for the log-mel transform
+ *      (vad/acoustics/transforms/log_mel_spectrogram.py:19-32:
+ *      np.log(librosa.feature.melspectrogram(y, sr, n_mels, n_fft, hop_length, win_length) + 1e-6),
+ *      librosa 0.8.0 defaults: periodic hann zero-padded to n_fft, center=True/reflect, power 2, Slaney mel).
+ *      librosa is not vendored by the reference: parity is pinned to the NumPy restatement of that
+ *      algorithm (oracle/logmel_oracle.py), not to librosa itself.  n_fft: power of two in [32, 4096].
+ *  audio   dev float [n_samples] mono PCM in [-1, 1]
+ *  feat    dev float [vadb_logmel_frames(n_samples, hop), n_mels]                                   */
+long vadb_logmel_frames(long n_samples, int hop);          /* 1 + n_samples / hop */
+int vadb_logmel(vadb_handle* h, const float* audio, long n_samples, int sample_rate, int n_fft, int hop,
+                int win, int n_mels, float* feat, void* stream);
+/* Host-only helper (no device needed): the dense [n_mels, n_fft/2+1] float32 mel filterbank and the
+ * [n_fft] float64 window the kernel uses; either output may be NULL. */
+int vadb_logmel_tables(int sample_rate, int n_fft, int win, int n_mels, float* fb_dense, double* window);
+
+/* ---- replaces VADFromScratchPredictor.predict_probabilities from the AUDIO on
+ *      (vad/predictor.py:159-262 including :160 feature extraction): H2D of the samples, log-mel,
+ *      window gather, forward, boosted aggregation, D2H -- one call, nothing but PCM crosses PCIe.
+ *  audio     host float [n_samples]; n_mels is the handle's feature_size
+ *  feat_out  host float [L, F] log-mel frames, L = vadb_logmel_frames(n_samples, hop)   (or NULL)
+ *  probs_LW  host float [L, W]                                                           (or NULL)
+ *  mean_L    host float [L]                                                              (or NULL) */
+int vadb_predict_audio_host(vadb_handle* h, const float* audio, long n_samples, int sample_rate, int n_fft,
+                            int hop, int win, int half, int jump, float* feat_out, float* probs_LW,
+                            float* mean_L);
+
 /* ---- individual stages, exported for kernel-level parity tests and the roofline bench ---- */
 /* Fused scaled-dot-product attention over the frame axis:
  * O = softmax(Q K^T / sqrt(128) [+ key padding mask]) V   (vad/modeling/transformer.py:351-363,

@@ -220,3 +220,29 @@ def test_log_mel_shapes_and_filterbank():
     assert feat.shape == (501, 80) and feat.dtype == np.float32     # 5 s -> 501 frames
     assert np.isfinite(feat).all() and feat.min() >= np.log(1e-6) - 1e-3
     assert abs(int(feat.mean(axis=0).argmax()) - 11) <= 1          # 440 Hz lands in mel band ~11
+
+
+def test_logmel_host_tables_match_oracle(lib):
+    """The mel filterbank and window the CUDA log-mel kernel uses are built on the host by the library
+    (csrc/k_logmel.cu::logmel_tables); they must be the NumPy restatement's, bit for bit."""
+    from oracle import logmel_oracle as LO
+    for sr, n_fft, win, n_mels in [(16000, 512, 400, 80), (16000, 512, 400, 64), (8000, 256, 200, 40),
+                                   (16000, 1024, 400, 128), (44100, 2048, 1102, 96)]:
+        fb = np.empty((n_mels, n_fft // 2 + 1), np.float32)
+        w = np.empty(n_fft, np.float64)
+        rc = lib.vadb_logmel_tables(sr, n_fft, win, n_mels, fb.ctypes.data_as(ctypes.c_void_p),
+                                    w.ctypes.data_as(ctypes.c_void_p))
+        assert rc == 0
+        np.testing.assert_array_equal(fb, LO.mel_filterbank(sr, n_fft, n_mels))
+        np.testing.assert_allclose(w, LO.padded_window(n_fft, win), rtol=0, atol=1e-15)
+    assert lib.vadb_logmel_tables(16000, 500, 400, 80, None, None) != 0          # n_fft not a power of two
+    assert lib.vadb_logmel_frames(80000, 160) == 501 and lib.vadb_logmel_frames(0, 160) == 1
+
+
+def test_logmel_oracle_matches_host_feature_extractor():
+    """oracle/logmel_oracle.py and the product's host-side FeatureExtractor restate the same algorithm."""
+    from oracle import logmel_oracle as LO
+    from vad_b200.features import log_mel_spectrogram
+    a = (np.random.default_rng(0).standard_normal(16000 * 2) * 0.1).astype(np.float32)
+    np.testing.assert_array_equal(LO.log_mel_frames(a, 16000, 512, 160, 400, 80),
+                                  log_mel_spectrogram(a, 16000, 512, 160, 400, 80).T)

@@ -233,3 +233,57 @@ def test_full_size_properties_config2():
     want = O.forward_prob(st, x[:2].cpu()).numpy()
     assert np.abs(prob[:2].cpu().numpy() - want).max() <= 1e-2
     eng.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# log-mel front end on the device -- pinned to the NumPy restatement of
+# librosa 0.8.0's algorithm (oracle/logmel_oracle.py); librosa itself is absent: parity unpinned there
+# ----------------------------------------------------------------------------------------------
+def _test_audio(seconds, seed, sr=16000):
+    rng = np.random.default_rng(seed)
+    t = np.arange(int(sr * seconds)) / sr
+    sig = 0.3 * np.sin(2 * np.pi * 220 * t) * (np.sin(2 * np.pi * 1.5 * t) > 0) \
+        + 0.05 * np.sin(2 * np.pi * 3100 * t) + 0.01 * rng.standard_normal(len(t))
+    sig[: sr // 4] = 0.0                                    # digital silence: exercises log(0 + 1e-6)
+    return sig.astype(np.float32)
+
+
+@pytest.mark.parametrize("sr,n_fft,hop,win,n_mels,seconds", [
+    (16000, 512, 160, 400, 80, 5.0),       # the reference configuration (tests/configs/vad/train_config.yaml)
+    (16000, 512, 160, 400, 64, 1.3),
+    (8000, 256, 80, 200, 40, 2.0),
+    (16000, 1024, 256, 1024, 128, 1.0),
+    (16000, 512, 160, 400, 80, 0.05),      # shorter than one window: reflect padding on both sides
+])
+def test_logmel_kernel_vs_oracle(sr, n_fft, hop, win, n_mels, seconds):
+    from oracle import logmel_oracle as LO
+    eng = engine_for(SYN, "bf16")
+    a = _test_audio(seconds, 1, sr)
+    want = LO.log_mel_frames(a, sr, n_fft, hop, win, n_mels)
+    got = eng.logmel(a, sr, n_fft, hop, win, n_mels)
+    got_dev = eng.logmel(torch.from_numpy(a).cuda(), sr, n_fft, hop, win, n_mels).cpu().numpy()
+    assert got.shape == want.shape == (1 + len(a) // hop, n_mels)
+    np.testing.assert_array_equal(got, got_dev)
+    err = np.abs(got - want).max()
+    print(f"logmel sr={sr} n_fft={n_fft} n_mels={n_mels} {seconds}s: max|d| = {err:.3e}")
+    # same float64 FFT and float32 roundings as the restatement: only summation order / 1-ulp log differ
+    assert err <= 2e-4
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_predict_audio_matches_oracle_pipeline(dtype):
+    """audio -> log-mel -> windows -> model -> boosted probabilities in ONE device call
+    (vad/predictor.py:159-262 including :160) against the oracle's feature extraction + predictor."""
+    from oracle import logmel_oracle as LO
+    from vad_b200.engine import VadEngine
+    st = O.make_state(3, 80, 3, 128)
+    eng = VadEngine.from_state_dict(st, compute_dtype=dtype)
+    a = _test_audio(3.0, 2)
+    feat = LO.log_mel_frames(a, 16000, 512, 160, 400, 80)
+    want = O.predict_probabilities(st, feat, 19, 9)
+    probs, mean, got_feat = eng.predict_audio(a, 16000, 512, 160, 400, 19, 9, want_features=True)
+    assert probs.shape == want.shape
+    assert np.abs(got_feat - feat).max() <= 2e-4
+    assert np.abs(probs - want).max() <= TOL[dtype]
+    np.testing.assert_allclose(mean, probs.mean(axis=1), atol=1e-6)
+    eng.close()

@@ -12,7 +12,8 @@ SYMBOLS = (
     "vadb_create", "vadb_destroy", "vadb_last_error", "vadb_weight_count", "vadb_load_weights",
     "vadb_reserve", "vadb_forward", "vadb_forward_host", "vadb_predict_probabilities",
     "vadb_predict_probabilities_host", "vadb_attention", "vadb_positional_table",
-    "vadb_launch_count", "vadb_version",
+    "vadb_launch_count", "vadb_version", "vadb_logmel_frames", "vadb_logmel", "vadb_logmel_tables",
+    "vadb_predict_audio_host",
 )
 
 
@@ -62,6 +63,14 @@ def load_library():
     lib.vadb_positional_table.restype = i32
     lib.vadb_launch_count.argtypes = [vp]
     lib.vadb_launch_count.restype = C.c_int64
+    lib.vadb_logmel_frames.argtypes = [C.c_long, i32]
+    lib.vadb_logmel_frames.restype = C.c_long
+    lib.vadb_logmel.argtypes = [vp, vp, C.c_long, i32, i32, i32, i32, i32, vp, vp]
+    lib.vadb_logmel.restype = i32
+    lib.vadb_logmel_tables.argtypes = [i32, i32, i32, i32, vp, vp]
+    lib.vadb_logmel_tables.restype = i32
+    lib.vadb_predict_audio_host.argtypes = [vp, vp, C.c_long, i32, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.vadb_predict_audio_host.restype = i32
     lib.vadb_version.argtypes = []
     lib.vadb_version.restype = C.c_char_p
     _lib = lib

@@ -680,6 +680,7 @@ cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o,
     if (n_pairs > grid && rem > 0 && 2 * rem <= grid) { n_full = n_pairs - rem; n_items = n_full + 2 * rem; }
   }
   static const int stagger = getenv("VADB_ATTN_STAGGER") ? atoi(getenv("VADB_ATTN_STAGGER")) : ATTN_DEFAULT_STAGGER;
+  (void)stagger;   // captured by the generic lambda below
   static const bool want_trace = getenv("VADB_ATTN_TRACE") != nullptr;
   static const int variant = getenv("VADB_ATTN_VARIANT") ? atoi(getenv("VADB_ATTN_VARIANT")) : ATTN_DEFAULT_VARIANT;
   auto run = [&](auto kern_trace, auto kern) -> cudaError_t {

@@ -82,6 +82,14 @@ struct vadb_handle {
   int32_t* dev_len = nullptr; size_t dev_len_n = 0;
   void* win_prob = nullptr; size_t win_prob_bytes = 0;   // [n, W] per-window probabilities
   void* win_proj = nullptr; size_t win_proj_bytes = 0;   // [L, 128] fp32 input projection of the whole clip
+
+  // log-mel front end (k_logmel.cu): device tables for one (sr, n_fft, win, n_mels) at a time
+  int lm_sr = 0, lm_nfft = 0, lm_win = 0, lm_nmels = 0;
+  double* lm_window = nullptr; double* lm_twiddle = nullptr;
+  int* lm_meta = nullptr;      // [3][n_mels]: first bin, number of bins, offset into lm_w
+  float* lm_w = nullptr;       // packed non-zero runs of the mel filterbank
+  void* lm_audio = nullptr; size_t lm_audio_bytes = 0;   // device copy of the audio (host entry point)
+  void* lm_feat = nullptr; size_t lm_feat_bytes = 0;     // [frames, n_mels] features (host entry point)
 };
 
 namespace {
@@ -437,6 +445,12 @@ void vadb_destroy(vadb_handle* h) {
   if (h->dev_len) cudaFree(h->dev_len);
   if (h->win_prob) cudaFree(h->win_prob);
   if (h->win_proj) cudaFree(h->win_proj);
+  if (h->lm_window) cudaFree(h->lm_window);
+  if (h->lm_twiddle) cudaFree(h->lm_twiddle);
+  if (h->lm_meta) cudaFree(h->lm_meta);
+  if (h->lm_w) cudaFree(h->lm_w);
+  if (h->lm_audio) cudaFree(h->lm_audio);
+  if (h->lm_feat) cudaFree(h->lm_feat);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->own_stream2) cudaStreamDestroy(h->own_stream2);
   for (int i = 0; i < 2; ++i) {
@@ -709,6 +723,124 @@ int vadb_predict_probabilities_host(vadb_handle* h, const float* feat, int L, in
   CU_TRY(h, cudaStreamSynchronize(s));
   if (probs_LW) memcpy(probs_LW, h->pin_out, (size_t)L * W * sizeof(float));
   if (mean_L) memcpy(mean_L, (float*)h->pin_out + (size_t)L * W, (size_t)L * sizeof(float));
+  return VADB_OK;
+}
+
+/* ---- log-mel front end ---- */
+long vadb_logmel_frames(long n_samples, int hop) { return (n_samples < 0 || hop <= 0) ? 0 : 1 + n_samples / hop; }
+
+int vadb_logmel_tables(int sample_rate, int n_fft, int win, int n_mels, float* fb_dense, double* window) {
+  if (sample_rate <= 0 || n_fft < 2 || (n_fft & (n_fft - 1)) || win <= 0 || win > n_fft || n_mels <= 0) return VADB_E_INVALID;
+  std::vector<float> fb;
+  std::vector<double> w;
+  logmel_tables(sample_rate, n_fft, win, n_mels, &fb, &w);
+  if (fb_dense) memcpy(fb_dense, fb.data(), fb.size() * sizeof(float));
+  if (window) memcpy(window, w.data(), w.size() * sizeof(double));
+  return VADB_OK;
+}
+
+static int ensure_logmel(vadb_handle* h, int sr, int n_fft, int win, int n_mels, cudaStream_t s) {
+  if (sr <= 0 || n_fft < 32 || n_fft > 4096 || (n_fft & (n_fft - 1)) || win <= 0 || win > n_fft || n_mels <= 0 || n_mels > 1024)
+    return fail(h, VADB_E_INVALID, "log-mel: n_fft must be a power of two in [32, 4096], 0 < win <= n_fft");
+  if (h->lm_sr == sr && h->lm_nfft == n_fft && h->lm_win == win && h->lm_nmels == n_mels) return VADB_OK;
+  std::vector<float> fb;
+  std::vector<double> window;
+  logmel_tables(sr, n_fft, win, n_mels, &fb, &window);
+  const int n_bins = n_fft / 2 + 1;
+  std::vector<int> meta(3 * (size_t)n_mels);
+  std::vector<float> packed;
+  for (int m = 0; m < n_mels; ++m) {
+    int first = -1, last = -1;
+    for (int k = 0; k < n_bins; ++k)
+      if (fb[(size_t)m * n_bins + k] != 0.f) { if (first < 0) first = k; last = k; }
+    meta[m] = first < 0 ? 0 : first;
+    meta[n_mels + m] = first < 0 ? 0 : last - first + 1;
+    meta[2 * n_mels + m] = (int)packed.size();
+    for (int k = meta[m]; k < meta[m] + meta[n_mels + m]; ++k) packed.push_back(fb[(size_t)m * n_bins + k]);
+  }
+  if (packed.empty()) packed.push_back(0.f);
+  std::vector<double> tw((size_t)n_fft);      // [n_fft/2] (cos, -sin)
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int k = 0; k < n_fft / 2; ++k) { tw[2 * k] = cos(two_pi * k / n_fft); tw[2 * k + 1] = -sin(two_pi * k / n_fft); }
+  cudaStreamSynchronize(s);                    // queued kernels may still read the old tables
+  if (h->lm_window) cudaFree(h->lm_window);
+  if (h->lm_twiddle) cudaFree(h->lm_twiddle);
+  if (h->lm_meta) cudaFree(h->lm_meta);
+  if (h->lm_w) cudaFree(h->lm_w);
+  h->lm_window = nullptr; h->lm_twiddle = nullptr; h->lm_meta = nullptr; h->lm_w = nullptr; h->lm_sr = 0;
+  CU_TRY(h, cudaMalloc(&h->lm_window, window.size() * sizeof(double)));
+  CU_TRY(h, cudaMalloc(&h->lm_twiddle, tw.size() * sizeof(double)));
+  CU_TRY(h, cudaMalloc(&h->lm_meta, meta.size() * sizeof(int)));
+  CU_TRY(h, cudaMalloc(&h->lm_w, packed.size() * sizeof(float)));
+  CU_TRY(h, cudaMemcpy(h->lm_window, window.data(), window.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CU_TRY(h, cudaMemcpy(h->lm_twiddle, tw.data(), tw.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CU_TRY(h, cudaMemcpy(h->lm_meta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CU_TRY(h, cudaMemcpy(h->lm_w, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->lm_sr = sr; h->lm_nfft = n_fft; h->lm_win = win; h->lm_nmels = n_mels;
+  return VADB_OK;
+}
+
+int vadb_logmel(vadb_handle* h, const float* audio, long n_samples, int sample_rate, int n_fft, int hop,
+                int win, int n_mels, float* feat, void* stream) {
+  if (!h) return VADB_E_INVALID;
+  if (!audio || !feat || n_samples <= 0 || hop <= 0) return fail(h, VADB_E_INVALID, "bad log-mel arguments");
+  DeviceGuard dg(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = ensure_logmel(h, sample_rate, n_fft, win, n_mels, s);
+  if (rc) return rc;
+  const long n_frames = vadb_logmel_frames(n_samples, hop);
+  cudaError_t e = launch_logmel(audio, n_samples, n_fft, hop, n_frames, h->lm_window, h->lm_twiddle, h->lm_meta,
+                                h->lm_meta + n_mels, h->lm_meta + 2 * n_mels, h->lm_w, n_mels, feat, s);
+  if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("logmel: ") + cudaGetErrorString(e));
+  h->launches++;
+  return VADB_OK;
+}
+
+int vadb_predict_audio_host(vadb_handle* h, const float* audio, long n_samples, int sample_rate, int n_fft,
+                            int hop, int win, int half, int jump, float* feat_out, float* probs_LW,
+                            float* mean_L) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!audio || n_samples <= 0 || hop <= 0 || half < 1 || jump < 1) return fail(h, VADB_E_INVALID, "bad audio arguments");
+  DeviceGuard dg(h->device);
+  cudaStream_t s = h->own_stream;
+  const int F = h->cfg.feature_size, W = window_W(half, jump);
+  const long L = vadb_logmel_frames(n_samples, hop);
+  if (L > 0x7fffffffL / (W + 1)) return fail(h, VADB_E_INVALID, "audio too long for one call (split it: split_max_seconds)");
+  const size_t a_bytes = (size_t)n_samples * sizeof(float);
+  if ((rc = ensure_bytes(h, &h->lm_audio, &h->lm_audio_bytes, a_bytes, false))) return rc;
+  if ((rc = ensure_bytes(h, &h->lm_feat, &h->lm_feat_bytes, (size_t)L * F * sizeof(float), false))) return rc;
+  // upload in chunks through the two pinned staging slots: the memcpy of chunk i+1 overlaps the DMA of chunk i
+  const size_t CH = (size_t)4 << 20;
+  if ((rc = ensure_bytes(h, &h->pin_in, &h->pin_in_bytes, 2 * CH, true))) return rc;
+  int n_ch = 0;
+  for (size_t off = 0; off < a_bytes; off += CH, ++n_ch) {
+    const size_t nb = std::min(CH, a_bytes - off);
+    const int slot = n_ch & 1;
+    char* stage = (char*)h->pin_in + (size_t)slot * CH;
+    if (n_ch >= 2) CU_TRY(h, cudaEventSynchronize(h->ev_h2d[slot]));
+    memcpy(stage, (const char*)audio + off, nb);
+    CU_TRY(h, cudaMemcpyAsync((char*)h->lm_audio + off, stage, nb, cudaMemcpyHostToDevice, s));
+    CU_TRY(h, cudaEventRecord(h->ev_h2d[slot], s));
+  }
+  if ((rc = vadb_logmel(h, (const float*)h->lm_audio, n_samples, sample_rate, n_fft, hop, win, F,
+                        (float*)h->lm_feat, s)))
+    return rc;
+  const size_t out_floats = (size_t)L * (W + 1);
+  const size_t feat_floats = feat_out ? (size_t)L * F : 0;
+  if ((rc = ensure_bytes(h, &h->pin_out, &h->pin_out_bytes, (out_floats + feat_floats) * sizeof(float), true))) return rc;
+  if ((rc = ensure_bytes(h, &h->dev_out, &h->dev_out_bytes, out_floats * sizeof(float), false))) return rc;
+  float* d_lw = (float*)h->dev_out;
+  float* d_mean = d_lw + (size_t)L * W;
+  if ((rc = vadb_predict_probabilities(h, (const float*)h->lm_feat, (int)L, half, jump, d_lw, d_mean, s))) return rc;
+  CU_TRY(h, cudaMemcpyAsync(h->pin_out, d_lw, out_floats * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (feat_out)
+    CU_TRY(h, cudaMemcpyAsync((float*)h->pin_out + out_floats, h->lm_feat, feat_floats * sizeof(float),
+                              cudaMemcpyDeviceToHost, s));
+  CU_TRY(h, cudaStreamSynchronize(s));
+  if (probs_LW) memcpy(probs_LW, h->pin_out, (size_t)L * W * sizeof(float));
+  if (mean_L) memcpy(mean_L, (float*)h->pin_out + (size_t)L * W, (size_t)L * sizeof(float));
+  if (feat_out) memcpy(feat_out, (float*)h->pin_out + out_floats, feat_floats * sizeof(float));
   return VADB_OK;
 }
 

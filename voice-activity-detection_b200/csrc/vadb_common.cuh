@@ -157,6 +157,12 @@ cudaError_t launch_window_gather_ln(const float* proj, const float* pe, float* o
                                     const float* ln_g, const float* ln_b, long n_rows, int W, int half,
                                     int jump, cudaStream_t s);
 
+// log-mel front end (k_logmel.cu): host-built tables and the per-frame FFT + mel + log kernel
+void logmel_tables(int sr, int n_fft, int win, int n_mels, std::vector<float>* fb_dense, std::vector<double>* window);
+cudaError_t launch_logmel(const float* audio, long n_samples, int n_fft, int hop, long n_frames, const double* window,
+                          const double* twiddle, const int* fb_start, const int* fb_len, const int* fb_off,
+                          const float* fb_w, int n_mels, float* out, cudaStream_t s);
+
 // misc element-wise (k_window.cu)
 cudaError_t launch_pad_rows_bf16(const float* in, bf16* out, int rows, int cols, cudaStream_t s);
 cudaError_t launch_f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t s);

@@ -195,6 +195,41 @@ class VadEngine:
         _cabi.check(self._lib, self._h, rc, "vadb_predict_probabilities_host")
         return probs, mean
 
+    def logmel(self, audio, sample_rate: int, n_fft: int, hop: int, win: int, n_mels: int):
+        """Log-mel frames [L, n_mels] of mono PCM (vad/acoustics/transforms/log_mel_spectrogram.py:19-32
+        + feature_extractor.py:77-80) computed on the device.  ``audio``: 1-D CUDA tensor -> CUDA
+        tensor; numpy / CPU tensor -> uploaded, result returned as numpy."""
+        on_dev = isinstance(audio, torch.Tensor) and audio.is_cuda
+        a = audio if on_dev else torch.as_tensor(np.ascontiguousarray(audio, dtype=np.float32)).to(self.device)
+        a = a.to(torch.float32).contiguous()
+        n = a.numel()
+        L = int(self._lib.vadb_logmel_frames(n, hop))
+        feat = torch.empty((L, n_mels), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self._lib.vadb_logmel(self._h, C.c_void_p(a.data_ptr()), n, sample_rate, n_fft, hop, win,
+                                       n_mels, C.c_void_p(feat.data_ptr()), self._stream_ptr())
+        _cabi.check(self._lib, self._h, rc, "vadb_logmel")
+        return feat if on_dev else feat.cpu().numpy()
+
+    def predict_audio(self, audio, sample_rate: int, n_fft: int, hop: int, win: int, half: int, jump: int,
+                      want_features: bool = False):
+        """Host PCM -> (probs [L,W], mean [L], features [L,F] or None), everything between on the
+        device in one call (vad/predictor.py:159-262 including the feature extraction of :160)."""
+        a = np.ascontiguousarray(np.asarray(audio, dtype=np.float32))
+        if a.ndim != 1:
+            raise ValueError("expected mono PCM [n_samples]")
+        W = 2 * (half - 1) // jump + 3
+        L = int(self._lib.vadb_logmel_frames(a.shape[0], hop))
+        probs = np.empty((L, W), dtype=np.float32)
+        mean = np.empty((L,), dtype=np.float32)
+        feat = np.empty((L, self.feature_size), dtype=np.float32) if want_features else None
+        rc = self._lib.vadb_predict_audio_host(
+            self._h, a.ctypes.data_as(C.c_void_p), a.shape[0], sample_rate, n_fft, hop, win, half, jump,
+            feat.ctypes.data_as(C.c_void_p) if want_features else None,
+            probs.ctypes.data_as(C.c_void_p), mean.ctypes.data_as(C.c_void_p))
+        _cabi.check(self._lib, self._h, rc, "vadb_predict_audio_host")
+        return probs, mean, feat
+
     def attention(self, q, k, v, lengths=None):
         """Stage-level entry (kernel parity tests / roofline bench): q,k,v [B,T,128] CUDA,
         fp32 -> CUDA-core kernel, bf16 -> tcgen05 kernel."""

@@ -7,7 +7,9 @@ power=2, Slaney mel scale with Slaney area normalisation, fmin=0, fmax=sr/2).
 
 librosa is not installed here and is not vendored by the reference, so this NumPy restatement of
 its published algorithm has no golden vectors: **parity unpinned** for this step (the north-star
-parity bar is stated "on identical log-mel inputs").  Host-side NumPy; a GPU version is future work.
+parity bar is stated "on identical log-mel inputs").  This module is the host-side (NumPy) FeatureExtractor
+of the reference API; the predictor itself runs the same transform on the device
+(csrc/k_logmel.cu via VadEngine.predict_audio / VadEngine.logmel) whenever n_fft is a power of two.
 """
 from __future__ import annotations
 

@@ -6,6 +6,7 @@ host<->device round trips).
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from datetime import timedelta
 from itertools import chain
@@ -77,13 +78,25 @@ class VADFromScratchPredictor:
         """-> positive-class probabilities [L, W] float32 (vad/predictor.py:159-262).
         Accepts AudioData (features are extracted first, :160) or an already extracted feature
         matrix [L, F] (numpy or tensor)."""
-        if isinstance(audio_data, AudioData):
-            feature = self.feature_extractor.extract_with_postprocessing(audio_data)
-        else:
-            feature = audio_data
         if self.config.model.name != "self-attention":
             raise NotImplementedError
         eng = self.model.engine(self.device)
+        if isinstance(audio_data, AudioData):
+            tr = self.feature_extractor.transform
+            n_fft = int(tr.n_fft)
+            if n_fft >= 32 and n_fft <= 4096 and (n_fft & (n_fft - 1)) == 0 and \
+                    os.environ.get("VADB_HOST_FEATURES", "0") != "1":
+                # audio -> log-mel -> windows -> model -> boosted probabilities, all on the device:
+                # only the PCM samples go up and the [L, W] probabilities come back
+                sr = audio_data.sample_rate
+                probs, _, _ = eng.predict_audio(audio_data.audio, sr, n_fft, int(tr.hop_ms / 1000 * sr),
+                                                int(tr.window_ms / 1000 * sr),
+                                                self.context_window_half_frames,
+                                                self.context_window_jump_frames)
+                return probs
+            feature = self.feature_extractor.extract_with_postprocessing(audio_data)
+        else:
+            feature = audio_data
         probs, _ = eng.predict_probabilities(feature, self.context_window_half_frames,
                                              self.context_window_jump_frames)
         if isinstance(probs, torch.Tensor):
