@@ -6,17 +6,22 @@
 // padding mask), :333 (softmax over keys), :338-346 (P V and the head merge) -- the three
 // [B,1,T,T] fp32 score tensors the reference materialises never leave the SM.
 //
-// Persistent CTAs (one per SM) walk a static list of work items; one item = one clip x 256 query rows
-// = two 128-row query tiles:
-//   warp 8      TMA producer: Q (once), a 4-stage ring of 64-key K tiles and a 3-stage ring of V
-//               tiles, all 128B-swizzled
-//   warp 9      MMA issuer (one elected lane): S_t = Q_t K^T and O_t += P_t V via tcgen05.mma with
-//               accumulators in TMEM -- S double-buffered per query tile (4 x 64 columns),
-//               O 2 x 128 columns.  Q K^T of step j+2 is issued right behind P V of step j, so the
-//               scores of the next step are already in TMEM when a softmax warpgroup finishes a step.
+// Persistent CTAs (one per SM, 11 warps) walk a static list of work items; one item = one clip x 256 query
+// rows = two 128-row query tiles (the last, partial round is split into single-tile items, and odd CTAs
+// run theirs first so that the CTAs do not all hit their item boundaries -- and the memory system --
+// together, see ItemWalk):
+//   warp 8      TMA producer: Q (once per item), 3-stage rings of 64-key K tiles and V tiles, all
+//               128B-swizzled; K runs two steps ahead of V
+//   warps 9,10  one MMA-issuing warp per query tile (one elected lane): S_t = Q_t K^T and O_t += P_t V via
+//               tcgen05.mma with accumulators in TMEM -- S double-buffered per query tile (4 x 64
+//               columns), O 2 x 128 columns.  Q K^T of step j+2 is issued right behind P V of step j, so
+//               the scores of the next step are already in TMEM when a softmax warpgroup finishes a step.
 //   warps 0-3   softmax warpgroup of query tile 0: one thread per query row (TMEM lane),
-//   warps 4-7   softmax warpgroup of query tile 1   tcgen05.ld S -> online softmax (fp32, exp2,
-//               lazy rescale of O in TMEM) -> P (bf16) into swizzled shared memory
+//   warps 4-7   softmax warpgroup of query tile 1   tcgen05.ld S -> online softmax (fp32, exp2, lazy
+//               rescale of O in TMEM) -> P (bf16) written back over the S buffer in TMEM and consumed
+//               by the P V MMA from there (TS form); steps are software-pipelined (the scores of step
+//               j+1 are loaded while the P hand-off of step j is in flight) and the two warpgroups take
+//               turns on the SFU through a named-barrier token
 // The two query tiles share every K/V tile and ping-pong on the tensor pipe.
 //
 // Algorithmic traffic per launch: read Q,K,V once + write O once = 4*B*T*128*2 bytes (SURVEY.md

@@ -568,6 +568,7 @@ int vadb_forward_host(vadb_handle* h, const float* x, const int32_t* lengths, in
     const int want = atoi(e);
     if (want >= 1) C = std::max(1, (B + want - 1) / want);
   }
+  // (sizes ramping up 5:8:9:10 instead of four equal chunks: modelled -5 %, measured +2 % -- not used)
   const int n_chunks = (B + C - 1) / C;
   const size_t n = (size_t)B * T;
   auto is_pinned = [](const void* p) {
