@@ -65,7 +65,8 @@ constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;   // slack for 1024-byte alig
 
 // barrier slots (8 bytes each) at OFF_BAR
 enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 5, B_VFULL = 9, B_VEMPTY = 12, B_SFULL = 15 /* [t][buf] */,
-       B_PFULL = 19, B_OFULL = 21, B_QEMPTY = 23, B_COUNT = 24 };
+       B_PFULL = 19, B_OFULL = 21, B_QEMPTY = 23, B_QFULL1 = 24, B_QEMPTY1 = 25, B_COUNT = 26 };
+static_assert(8 * B_COUNT <= 256, "barrier region");
 static_assert(8 * B_COUNT <= 256, "barrier region");
 static_assert(NK <= 4 && NV <= 3, "barrier slots");
 
@@ -203,8 +204,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     trace[2042] = (long long)gt;
   }
   if (threadIdx.x == 0) {
-    mbar_init(BAR(B_QFULL), 1);
-    mbar_init(BAR(B_QEMPTY), 2);                 // one arrival per MMA-issuing warp
+    // the Q buffer of each query tile is its own single-slot channel: tile 0's Q of the next item is
+    // requested as soon as tile 0's last Q K^T has retired, without waiting for tile 1
+    mbar_init(BAR(B_QFULL), 1); mbar_init(BAR(B_QFULL1), 1);
+    mbar_init(BAR(B_QEMPTY), 1); mbar_init(BAR(B_QEMPTY1), 1);
     for (int s = 0; s < NK; ++s) { mbar_init(BAR(B_KFULL + s), 1); mbar_init(BAR(B_KEMPTY + s), 2); }
     for (int s = 0; s < NV; ++s) { mbar_init(BAR(B_VFULL + s), 1); mbar_init(BAR(B_VEMPTY + s), 2); }
     for (int i = 0; i < 4; ++i) mbar_init(BAR(B_SFULL + i), 1);
@@ -232,19 +235,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   if (warp == 8) {
     // ======================= TMA producer =======================
     if (lane == 0) {
-      int kc = 0, vc = 0, nq = 0;              // K tiles / V tiles / Q loads issued so far
+      int kc = 0, vc = 0, nq[2] = {0, 0};      // K tiles / V tiles / Q loads (per query tile) issued so far
       const ItemWalk walk(n_items, n_full, stagger);
       for (int r = 0; r < walk.n; ++r) {
         const int idx = walk.idx(r);
         const Item it = get_item(idx, n_full, npairs, T, lengths);
         if (!it.valid || it.nkv == 0) continue;
-        mbar_wait(BAR(B_QEMPTY), (nq & 1) ^ 1, 1);            // every Q K^T of the previous item retired
-        mbar_arrive_expect_tx(BAR(B_QFULL), it.ntile * Q_TILE_BYTES);
-        for (int t = 0; t < it.ntile; ++t)
-          for (int hf = 0; hf < 2; ++hf)
-            tma_load_3d(smem_base + OFF_Q + t * Q_TILE_BYTES + hf * Q_HALF_BYTES, &tm_q, BAR(B_QFULL),
-                        hf * 64, it.q0 + t * BM, it.b);
-        ++nq;
         auto load_k = [&](int j) {
           const int ks = (kc + j) % NK;
           mbar_wait(BAR(B_KEMPTY + ks), (((kc + j) / NK) & 1) ^ 1, 2);
@@ -253,8 +249,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           tma_load_3d(kdst, &tm_k, BAR(B_KFULL + ks), 0, j * BKV, it.b);
           tma_load_3d(kdst + KV_HALF_BYTES, &tm_k, BAR(B_KFULL + ks), 64, j * BKV, it.b);
         };
-        // K runs two steps ahead of V, in the order the MMA warp consumes them
+        auto load_q = [&](int t) {
+          const uint32_t qe = BAR(t == 0 ? B_QEMPTY : B_QEMPTY1), qf = BAR(t == 0 ? B_QFULL : B_QFULL1);
+          mbar_wait(qe, (nq[t] & 1) ^ 1, 1);                  // every Q_t K^T of the previous item retired
+          mbar_arrive_expect_tx(qf, Q_TILE_BYTES);
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_3d(smem_base + OFF_Q + t * Q_TILE_BYTES + hf * Q_HALF_BYTES, &tm_q, qf, hf * 64,
+                        it.q0 + t * BM, it.b);
+          ++nq[t];
+        };
+        // Q of tile 0 and the first K tile first (all the first Q K^T needs), then tile 1's Q; K runs two
+        // steps ahead of V, in the order the MMA warps consume them
+        load_q(0);
         load_k(0);
+        if (it.ntile > 1) load_q(1);
         if (it.nkv > 1) load_k(1);
         for (int j = 0; j < it.nkv; ++j) {
           if (j + 2 < it.nkv) load_k(j + 2);
@@ -274,10 +282,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     // of one tile never queues behind the (blocking, tensor-pipe back-pressured) issue of the other
     // tile; with a single issuer the pipe idled ~600 of every ~1950 cycles (profiles/r1_attention_notes.md).
     // The whole warp walks the schedule (waits included) and one elected lane issues, so the
-    // descriptor arithmetic stays warp-uniform and costs an add or two per MMA.  The K/V/Q "empty"
+    // descriptor arithmetic stays warp-uniform and costs an add or two per MMA.  The K/V "empty"
     // barriers count one arrival per issuing warp; on single-tile items the idle warp keeps the
     // protocol uniform with plain arrivals (always behind its own wait on the matching "full" barrier,
-    // so it cannot run a phase ahead).
+    // so it cannot run a phase ahead).  Each query tile's Q buffer has its own full/empty pair.
     const int t = warp - 9;
     const uint32_t q_lo = desc_lo(smem_base + OFF_Q, 16);
     const uint32_t k_lo = desc_lo(smem_base + OFF_K, 16);
@@ -321,8 +329,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       const int nkv = it.nkv;
       const bool live = t < it.ntile;           // this warp's query tile exists in the item
       if (t == 0) TR(0);
-      mbar_wait(BAR(B_QFULL), nq & 1, 4);
-      ++nq;
+      const uint32_t q_empty = BAR(t == 0 ? B_QEMPTY : B_QEMPTY1);
+      if (live) {
+        mbar_wait(BAR(t == 0 ? B_QFULL : B_QFULL1), nq & 1, 4);
+        ++nq;
+      }
       // prologue: scores of steps 0 and 1
       for (int j = 0; j < 2 && j < nkv; ++j) {
         const int ks = (kc + j) % NK;
@@ -333,11 +344,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             issue_qk(ks, (g + j) & 1);
             umma_commit(BAR(B_SFULL + 2 * t + ((g + j) & 1)));
             umma_commit(BAR(B_KEMPTY + ks));
-            if (j == nkv - 1) umma_commit(BAR(B_QEMPTY));
+            if (j == nkv - 1) umma_commit(q_empty);
           }
         } else if (lane == 0) {
           mbar_arrive(BAR(B_KEMPTY + ks));
-          if (j == nkv - 1) mbar_arrive(BAR(B_QEMPTY));
         }
         __syncwarp();
       }
@@ -362,7 +372,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
               issue_qk(kn, (g + j) & 1);
               umma_commit(BAR(B_SFULL + 2 * t + ((g + j) & 1)));
               umma_commit(BAR(B_KEMPTY + kn));
-              if (j + 2 == nkv - 1) umma_commit(BAR(B_QEMPTY));   // last Q K^T of this item issued
+              if (j + 2 == nkv - 1) umma_commit(q_empty);   // last Q_t K^T of this item issued
             }
           }
         } else {
@@ -372,7 +382,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             mbar_arrive(BAR(B_VEMPTY + vs));
             if (more) {
               mbar_arrive(BAR(B_KEMPTY + kn));
-              if (j + 2 == nkv - 1) mbar_arrive(BAR(B_QEMPTY));
             }
           }
         }
