@@ -185,7 +185,8 @@ def main():
         return run_reference(args)
 
     import torch.distributed as dist
-    from oracle import vad_oracle as O                      # weights/inputs factory + cpu_baseline leg
+    from vad_b200 import synthetic as S                     # random-init weights (product side; the oracle is
+                                                            # only imported by the cpu_baseline / reference legs)
     from vad_b200.distributed import load_engine_from_broadcast
     from vad_b200.engine import VadEngine
 
@@ -205,7 +206,7 @@ def main():
 
     # ---- model: random-init weights of the named architecture; ONE broadcast at load ----
     eng = VadEngine(F, L, D, args.dtype, dev)
-    load_engine_from_broadcast(eng, O.make_state(0, F, L, D) if rank == 0 else None, src=0)
+    load_engine_from_broadcast(eng, S.random_state(0, F, L, D) if rank == 0 else None, src=0)
     eng.reserve(B_PER_GPU, T)
 
     # ---- synthetic inputs: N_ROT distinct batches (> L2) rotated between iterations ----

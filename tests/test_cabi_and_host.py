@@ -246,3 +246,14 @@ def test_logmel_oracle_matches_host_feature_extractor():
     a = (np.random.default_rng(0).standard_normal(16000 * 2) * 0.1).astype(np.float32)
     np.testing.assert_array_equal(LO.log_mel_frames(a, 16000, 512, 160, 400, 80),
                                   log_mel_spectrogram(a, 16000, 512, 160, 400, 80).T)
+
+
+def test_product_synthetic_factories_match_the_oracle():
+    """bench.py's GPU arm draws its random weights / inputs from the product package
+    (vad_b200.synthetic), its cpu_baseline leg from the oracle: both must be the same model and data."""
+    from vad_b200 import synthetic as S
+    for F in (64, 80):
+        a, b = O.make_state(0, F, 3, 128), S.random_state(0, F, 3, 128)
+        assert list(a.keys()) == list(b.keys())
+        assert all(torch.equal(a[k], b[k]) for k in a)
+    assert torch.equal(O.make_input(1, 2, 16, 64), S.random_features(1, 2, 16, 64))

@@ -4,10 +4,10 @@ cases = [(1, 64), (1, 128), (1, 256), (2, 512), (3, 300)]
 code = r'''
 import sys, torch, numpy as np
 sys.path.insert(0, %r)
-from oracle import vad_oracle as O
+from vad_b200 import synthetic as S
 from vad_b200.engine import VadEngine
 B, T = %d, %d
-eng = VadEngine.from_state_dict(O.make_state(0, 64, 3, 128), compute_dtype="bf16")
+eng = VadEngine.from_state_dict(S.random_state(0, 64, 3, 128), compute_dtype="bf16")
 g = torch.Generator().manual_seed(0)
 q, k, v = (torch.randn(B, T, 128, generator=g).cuda().to(torch.bfloat16) for _ in range(3))
 o = eng.attention(q, k, v)

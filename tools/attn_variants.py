@@ -5,9 +5,9 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 code = r'''
 import sys, os, torch, numpy as np
 sys.path.insert(0, %r)
-from oracle import vad_oracle as O
+from vad_b200 import synthetic as S
 from vad_b200.engine import VadEngine
-eng = VadEngine.from_state_dict(O.make_state(0, 64, 3, 128), compute_dtype="bf16")
+eng = VadEngine.from_state_dict(S.random_state(0, 64, 3, 128), compute_dtype="bf16")
 g = torch.Generator().manual_seed(0)
 worst = 0.0
 for (B, T, lens) in [(1, 64, None), (2, 512, None), (3, 300, [300, 17, 129]), (2, 1024, [1024, 700])]:

@@ -2,12 +2,12 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import vad_oracle as O
+from vad_b200 import synthetic as S
 from vad_b200.engine import VadEngine
 
 B, T = int(os.environ.get("B", 256)), int(os.environ.get("T", 512))
 iters = int(os.environ.get("ITERS", 5))
-eng = VadEngine.from_state_dict(O.make_state(0, 64, 3, 128), compute_dtype="bf16")
+eng = VadEngine.from_state_dict(S.random_state(0, 64, 3, 128), compute_dtype="bf16")
 g = torch.Generator().manual_seed(0)
 sets = [tuple(torch.randn(B, T, 128, generator=g).cuda().to(torch.bfloat16) for _ in range(3)) for _ in range(3)]
 for i in range(3):

@@ -1,15 +1,16 @@
-"""Time the whole reference-predictor path from PCM: audio -> log-mel -> windows -> model -> boosted
+"""(developer tool; uses the test oracle's NumPy log-mel only as the host-side comparison)
+Time the whole reference-predictor path from PCM: audio -> log-mel -> windows -> model -> boosted
 probabilities (vad/predictor.py:159-262), device front end vs the host (NumPy) feature extraction."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-from oracle import vad_oracle as O
+from vad_b200 import synthetic as S
 from oracle import logmel_oracle as LO
 from vad_b200.engine import VadEngine
 
 seconds = float(os.environ.get("SECONDS_AUDIO", 600))
-st = O.make_state(3, 80, 3, 128)
+st = S.random_state(3, 80, 3, 128)
 eng = VadEngine.from_state_dict(st, compute_dtype="bf16")
 a = (np.random.default_rng(0).standard_normal(int(16000 * seconds)) * 0.1).astype(np.float32)
 for _ in range(2):

@@ -2,7 +2,7 @@
 import os, sys, time, subprocess, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import vad_oracle as O
+from vad_b200 import synthetic as S
 
 def ev_time(fn, iters=10, warm=3):
     for _ in range(warm): fn()
@@ -22,9 +22,9 @@ def wall(fn, iters=10, warm=3):
 
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     from vad_b200.engine import VadEngine
-    st = O.make_state(0, 64, 3, 128)
+    st = S.random_state(0, 64, 3, 128)
     eng = VadEngine.from_state_dict(st, compute_dtype="bf16")
-    xs = [O.make_input(i, 256, 512, 64).pin_memory() for i in range(3)]
+    xs = [S.random_features(i, 256, 512, 64).pin_memory() for i in range(3)]
     k = [0]
     def f():
         k[0] += 1
@@ -38,10 +38,10 @@ out["h2d_33MB_ms"] = ev_time(lambda: d.copy_(h, non_blocking=True))
 hp = torch.empty(256, 512).pin_memory(); dp = torch.empty_like(hp, device="cuda")
 out["d2h_0.5MB_ms"] = ev_time(lambda: hp.copy_(dp, non_blocking=True))
 from vad_b200.engine import VadEngine
-st = O.make_state(0, 64, 3, 128)
+st = S.random_state(0, 64, 3, 128)
 eng = VadEngine.from_state_dict(st, compute_dtype="bf16")
 for B in (32, 37, 64, 74, 86, 111, 128, 148, 256):
-    x = O.make_input(1, B, 512, 64).cuda()
+    x = S.random_features(1, B, 512, 64).cuda()
     out[f"dev_forward_B{B}_ms"] = ev_time(lambda: eng.forward(x, want_logp=False))
     out[f"dev_forward_B{B}_wall_ms"] = wall(lambda: eng.forward(x, want_logp=False))
 eng.close()

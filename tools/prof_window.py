@@ -4,12 +4,12 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-from oracle import vad_oracle as O
+from vad_b200 import synthetic as S
 from vad_b200.engine import VadEngine
 
 L = int(os.environ.get("L", 60000))          # 10 minutes of audio at 100 frames/s
 iters = int(os.environ.get("ITERS", 10))
-st = O.make_state(3, 80, 3, 128)
+st = S.random_state(3, 80, 3, 128)
 eng = VadEngine.from_state_dict(st, compute_dtype=os.environ.get("DTYPE", "bf16"))
 feat = (torch.randn(L, 80, generator=torch.Generator().manual_seed(0)) * 2 - 3)
 fd = feat.cuda()
