@@ -179,7 +179,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
             mbar_wait(BAR(BAR_REMPTY), (n & 1) ^ 1, 18);
             mbar_arrive_expect_tx(BAR(BAR_RFULL), RES_BYTES);
             for (int c = 0; c < 4; ++c)
-              tma_load_2d(smem_base + off_r + c * (RES_BYTES / 4), &tm_o2, BAR(BAR_RFULL), c * 32, tile * 128);
+              tma_load_2d(smem_base + off_r + c * (RES_BYTES / 4), &tm_o2, BAR(BAR_RFULL), c * 32,
+                          p.res_mod > 0 ? (tile * 128) % p.res_mod : tile * 128);
           }
         }
       }
@@ -556,7 +557,9 @@ cudaError_t launch_gemm_tc(const GemmTcArgs& a, int num_sms, cudaStream_t s, std
   p.bias = a.bias; p.relu = a.relu; p.residual = a.residual; p.res_mod = a.res_mod;
   p.out_f32 = a.out_f32; p.out_split = a.out[1] != nullptr && !a.emit_ln_g;
   p.emit_g = a.emit_ln_g; p.emit_b = a.emit_ln_b;
-  p.res_tma = (a.residual && a.res_mod == 0 && !p.prod && a.out_f32) ? 1 : 0;
+  // residual tiles by TMA: the residual stream itself, or the positional-encoding table when a 128-row tile
+  // never wraps around it (res_mod % 128 == 0: row (tile * 128) % res_mod onwards is contiguous)
+  p.res_tma = (a.residual && (a.res_mod == 0 || a.res_mod % 128 == 0) && !p.prod && a.out_f32) ? 1 : 0;
   for (int j = 0; j < 3; ++j) p.out_ptr[j] = a.out[j] ? a.out[j] : a.out[0];
   if (a.emit_ln_g && !(a.out_f32 && a.N == 128 && a.out[1])) return bad("LayerNorm emit needs fp32 N == 128 output + out[1]");
   const uint32_t w_bytes = (uint32_t)(a.N / 128) * (a.K / 128) * BLK_BYTES;
@@ -592,7 +595,7 @@ cudaError_t launch_gemm_tc(const GemmTcArgs& a, int num_sms, cudaStream_t s, std
     if (a.emit_ln_g && j == 1)       // bf16 LayerNorm copy [M,128]
       r = make_tmap_2d(&to[j], optr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, 128, 64, 32);
     else if (p.res_tma && j == 2)    // residual load map: 128-row boxes of 32 fp32 columns
-      r = make_tmap_2d(&to[j], a.residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, 128, 32, 128);
+      r = make_tmap_2d(&to[j], a.residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.res_mod > 0 ? a.res_mod : a.M, 128, 32, 128);
     else
       r = a.out_f32 ? make_tmap_2d(&to[j], optr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, ocols, 32, 32)
                     : make_tmap_2d(&to[j], optr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, ocols, 64, 32);
