@@ -197,10 +197,13 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # keep stdout to the ONE JSON line: anything else written to fd 1 from here on (NCCL prints its
+    # "NCCL version ..." banner there when the box exports NCCL_DEBUG) is routed to stderr, and the JSON
+    # line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
-        # keep stdout to the ONE JSON line: NCCL's own banner ("NCCL version ...", printed when the box
-        # exports NCCL_DEBUG=VERSION/INFO) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
@@ -344,7 +347,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 
