@@ -169,3 +169,35 @@ def test_small_T_fragment_mapping_reproduces_attention(T):
         s[b, :, L:] = -np.inf
     want = (torch.softmax(s, -1) @ v).numpy()
     assert np.abs(got - want).max() <= 1e-12
+
+
+def test_logmel_fft_indexing_model():
+    """csrc/k_logmel.cu: bit-reversed load + radix-2 DIT stages with the twiddle index j * (n/2 >> (s-1)),
+    and the reflect-padded frame indexing, restated in NumPy."""
+    def brev(i, bits):
+        return int(format(i, f"0{bits}b")[::-1], 2)
+    for n in (32, 512):
+        log2n, half = n.bit_length() - 1, n // 2
+        x = np.random.default_rng(n).standard_normal(n)
+        tw = np.exp(-2j * np.pi * np.arange(half) / n)
+        data = np.zeros(n, complex)
+        for i in range(n):
+            data[brev(i, log2n)] = x[i]
+        for s in range(1, log2n + 1):
+            hs, tstride = 1 << (s - 1), half >> (s - 1)
+            for b in range(half):
+                j = b & (hs - 1)
+                i0 = ((b >> (s - 1)) << s) + j
+                u, v = data[i0], data[i0 + hs] * tw[j * tstride]
+                data[i0], data[i0 + hs] = u + v, u - v
+        assert np.abs(data[:half + 1] - np.fft.rfft(x)).max() <= 1e-11
+    n_samples, hop, n_fft = 1000, 160, 512
+    a = np.arange(n_samples, dtype=np.float32)
+    y = np.pad(a, n_fft // 2, mode="reflect")
+    L = 1 + (len(y) - n_fft) // hop
+    assert L == 1 + n_samples // hop
+    for t in range(L):
+        m = t * hop + np.arange(n_fft) - n_fft // 2
+        m = np.where(m < 0, -m, m)
+        m = np.where(m >= n_samples, 2 * (n_samples - 1) - m, m)
+        np.testing.assert_array_equal(a[m], y[t * hop:t * hop + n_fft])
