@@ -94,6 +94,16 @@ int vadb_forward(vadb_handle* h, const void* x, int x_dtype, const int32_t* leng
 int vadb_forward_host(vadb_handle* h, const float* x, const int32_t* lengths, int B, int T,
                       float* prob, float* logp);
 
+/* Asynchronous form for streaming many batches: everything (H2D, forward, D2H) is only enqueued on the
+ * library's streams and the call returns at once, so the upload of the next batch overlaps the compute of
+ * this one (throughput = max(upload, compute) instead of their pipelined sum).  x, prob and logp must be
+ * PINNED host buffers and stay valid/untouched until vadb_host_wait(h, ticket) has returned; at most four
+ * calls may be outstanding.  Same reference interface as vadb_forward_host, called in a loop over batches
+ * (vad/predictor.py:182-258 iterates chunks of windows the same way, synchronously). */
+int vadb_forward_host_async(vadb_handle* h, const float* x, const int32_t* lengths, int B, int T,
+                            float* prob, float* logp, long* ticket);
+int vadb_host_wait(vadb_handle* h, long ticket);
+
 /* ---- replaces VADFromScratchPredictor.predict_probabilities from the feature matrix on
  *      (vad/predictor.py:169-262): window gather (:180-220), batched forward (:221-225)
  *      and boosted aggregation incl. the 0.5 fill of never-written slots (:238-258).

@@ -287,3 +287,25 @@ def test_predict_audio_matches_oracle_pipeline(dtype):
     assert np.abs(probs - want).max() <= TOL[dtype]
     np.testing.assert_allclose(mean, probs.mean(axis=1), atol=1e-6)
     eng.close()
+
+
+def test_forward_async_matches_blocking_host_call():
+    """Streaming host call (vadb_forward_host_async): several batches in flight, results identical to the
+    blocking call, tickets waited out of order, then a blocking call with another chunking in between."""
+    eng = engine_for(SYN, "bf16")
+    xs = [O.make_input(40 + i, 24, 128, 64).pin_memory() for i in range(6)]
+    want = [eng.forward(x, want_logp=False)[0].clone() for x in xs]
+    tickets = [eng.forward_async(x) for x in xs[:4]]          # four outstanding calls (the ring depth)
+    got = [None] * 6
+    for i in (1, 0, 3, 2):
+        got[i] = tickets[i].wait()[0].clone()
+    t4 = eng.forward_async(xs[4], want_logp=True)
+    mid = eng.forward(O.make_input(99, 5, 64, 64), want_logp=False)[0]      # blocking call, other shape
+    t5 = eng.forward_async(xs[5])
+    p4, lp4 = t4.wait()
+    got[4], got[5] = p4.clone(), t5.wait()[0].clone()
+    for i in range(6):
+        torch.testing.assert_close(got[i], want[i], rtol=0, atol=0)
+    assert lp4.shape == (24, 128, 2) and torch.isfinite(lp4).all() and torch.isfinite(mid).all()
+    with pytest.raises(ValueError):
+        eng.forward_async(O.make_input(1, 2, 16, 64))          # not pinned

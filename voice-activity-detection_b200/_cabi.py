@@ -13,7 +13,7 @@ SYMBOLS = (
     "vadb_reserve", "vadb_forward", "vadb_forward_host", "vadb_predict_probabilities",
     "vadb_predict_probabilities_host", "vadb_attention", "vadb_positional_table",
     "vadb_launch_count", "vadb_version", "vadb_logmel_frames", "vadb_logmel", "vadb_logmel_tables",
-    "vadb_predict_audio_host",
+    "vadb_predict_audio_host", "vadb_forward_host_async", "vadb_host_wait",
 )
 
 
@@ -71,6 +71,10 @@ def load_library():
     lib.vadb_logmel_tables.restype = i32
     lib.vadb_predict_audio_host.argtypes = [vp, vp, C.c_long, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.vadb_predict_audio_host.restype = i32
+    lib.vadb_forward_host_async.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.POINTER(C.c_long)]
+    lib.vadb_forward_host_async.restype = i32
+    lib.vadb_host_wait.argtypes = [vp, C.c_long]
+    lib.vadb_host_wait.restype = i32
     lib.vadb_version.argtypes = []
     lib.vadb_version.restype = C.c_char_p
     _lib = lib

@@ -75,6 +75,9 @@ struct vadb_handle {
   // host-call staging
   cudaStream_t own_stream = nullptr, own_stream2 = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_call[4] = {nullptr, nullptr, nullptr, nullptr};   // completion of the last four asynchronous host calls
+  long call_seq = 0, chunk_seq = 0;
+  size_t last_chunk_in = 0;
   void* pin_in = nullptr; size_t pin_in_bytes = 0;
   void* pin_out = nullptr; size_t pin_out_bytes = 0;
   void* dev_in = nullptr; size_t dev_in_bytes = 0;
@@ -424,6 +427,7 @@ int vadb_create(vadb_handle** out, const vadb_config* cfg, int device) {
     e = cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
   }
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->ev_call[i], cudaEventDisableTiming);
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete h; return fail(nullptr, VADB_E_CUDA, m); }
   *out = h;
   return VADB_OK;
@@ -457,6 +461,8 @@ void vadb_destroy(vadb_handle* h) {
     if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
   }
+  for (int i = 0; i < 4; ++i)
+    if (h->ev_call[i]) cudaEventDestroy(h->ev_call[i]);
   delete h;
 }
 
@@ -547,11 +553,14 @@ int vadb_forward(vadb_handle* h, const void* x, int x_dtype, const int32_t* leng
   return VADB_OK;
 }
 
-int vadb_forward_host(vadb_handle* h, const float* x, const int32_t* lengths, int B, int T,
-                      float* prob, float* logp) {
+// Shared body of vadb_forward_host (ticket == nullptr: returns when the outputs are in host memory) and
+// vadb_forward_host_async (ticket != nullptr: everything is only enqueued; pinned buffers required).
+static int forward_host_impl(vadb_handle* h, const float* x, const int32_t* lengths, int B, int T,
+                             float* prob, float* logp, long* ticket) {
   int rc = check_ready(h);
   if (rc) return rc;
   if (!x || B < 0 || T < 0) return fail(h, VADB_E_INVALID, "bad forward arguments");
+  if (ticket) *ticket = -1;
   if (B == 0 || T == 0) return VADB_OK;
   DeviceGuard dg(h->device);
   // Chunked two-stream pipeline: the H2D copy of clip chunk i+1 overlaps the forward of chunk i
@@ -564,6 +573,7 @@ int vadb_forward_host(vadb_handle* h, const float* x, const int32_t* lengths, in
   int C = (int)std::max<size_t>(1, ((size_t)8 << 20) / std::max<size_t>(clip_in, 1));
   C = std::max(C, (B + 3) / 4);
   C = std::min(C, B);
+  if (ticket) C = std::max(1, (B + 1) / 2);           // asynchronous calls overlap ACROSS calls: two chunks suffice
   if (const char* e = getenv("VADB_HOST_CHUNKS")) {    // tuning knob: force the number of chunks
     const int want = atoi(e);
     if (want >= 1) C = std::max(1, (B + want - 1) / want);
@@ -578,7 +588,15 @@ int vadb_forward_host(vadb_handle* h, const float* x, const int32_t* lengths, in
   };
   const bool in_pinned = is_pinned(x);
   const bool out_pinned = (!prob || is_pinned(prob)) && (!logp || is_pinned(logp));
+  if (ticket && !(in_pinned && out_pinned))
+    return fail(h, VADB_E_INVALID, "asynchronous host calls need pinned (page-locked) input and output buffers");
   const size_t chunk_in = (size_t)C * clip_in;
+  if (chunk_in != h->last_chunk_in) {
+    // the two device input slots are laid out by chunk size: a call with another chunk size must not
+    // upload over slots an outstanding asynchronous call is still reading
+    CU_TRY(h, cudaStreamSynchronize(s_comp));
+    h->last_chunk_in = chunk_in;
+  }
   if (!in_pinned && (rc = ensure_bytes(h, &h->pin_in, &h->pin_in_bytes, 2 * chunk_in, true))) return rc;
   if (!out_pinned && (rc = ensure_bytes(h, &h->pin_out, &h->pin_out_bytes, n * 3 * sizeof(float), true))) return rc;
   if ((rc = ensure_bytes(h, &h->dev_in, &h->dev_in_bytes, 2 * chunk_in, false))) return rc;
@@ -601,12 +619,15 @@ int vadb_forward_host(vadb_handle* h, const float* x, const int32_t* lengths, in
   float* hprob = out_pinned ? prob : (float*)h->pin_out;
   float* hlogp = out_pinned ? logp : (float*)h->pin_out + n;
   for (int i = 0; i < n_chunks; ++i) {
-    const int b0 = i * C, Bc = std::min(C, B - b0), slot = i & 1;
+    // the two device input slots alternate per chunk ACROSS calls, so an asynchronous call can upload
+    // while the previous call still computes
+    const int b0 = i * C, Bc = std::min(C, B - b0), slot = (int)((h->chunk_seq + i) & 1);
     const size_t bytes = (size_t)Bc * clip_in;
     const char* src = (const char*)x + (size_t)b0 * clip_in;
     char* dsti = (char*)h->dev_in + (size_t)slot * chunk_in;
-    // device slot free once the forward of chunk i-2 has consumed it
-    if (i >= 2) CU_TRY(h, cudaStreamWaitEvent(s_copy, h->ev_done[slot], 0));
+    // device slot free once the forward of the chunk that used it last (two chunks ago, possibly in the
+    // previous call) has consumed it; a never-recorded event does not block
+    CU_TRY(h, cudaStreamWaitEvent(s_copy, h->ev_done[slot], 0));
     if (!in_pinned) {
       char* stage = (char*)h->pin_in + (size_t)slot * chunk_in;
       if (i >= 2) CU_TRY(h, cudaEventSynchronize(h->ev_h2d[slot]));   // staging slot copied out
@@ -626,12 +647,38 @@ int vadb_forward_host(vadb_handle* h, const float* x, const int32_t* lengths, in
     if (logp) CU_TRY(h, cudaMemcpyAsync(hlogp + (size_t)b0 * T * 2, dlogp + (size_t)b0 * T * 2,
                                         (size_t)Bc * T * 2 * sizeof(float), cudaMemcpyDeviceToHost, s_comp));
   }
+  h->chunk_seq += n_chunks;
+  if (ticket) {                      // results land in the caller's pinned buffers; vadb_host_wait(ticket)
+    CU_TRY(h, cudaEventRecord(h->ev_call[h->call_seq & 3], s_comp));
+    *ticket = h->call_seq++;
+    return VADB_OK;
+  }
   CU_TRY(h, cudaStreamSynchronize(s_comp));
   CU_TRY(h, cudaStreamSynchronize(s_copy));
   if (!out_pinned) {
     if (prob) memcpy(prob, hprob, n * sizeof(float));
     if (logp) memcpy(logp, hlogp, 2 * n * sizeof(float));
   }
+  return VADB_OK;
+}
+
+int vadb_forward_host(vadb_handle* h, const float* x, const int32_t* lengths, int B, int T,
+                      float* prob, float* logp) {
+  return forward_host_impl(h, x, lengths, B, T, prob, logp, nullptr);
+}
+
+int vadb_forward_host_async(vadb_handle* h, const float* x, const int32_t* lengths, int B, int T,
+                            float* prob, float* logp, long* ticket) {
+  if (!ticket) return h ? fail(h, VADB_E_INVALID, "ticket must not be NULL") : VADB_E_INVALID;
+  return forward_host_impl(h, x, lengths, B, T, prob, logp, ticket);
+}
+
+int vadb_host_wait(vadb_handle* h, long ticket) {
+  if (!h) return VADB_E_INVALID;
+  if (ticket < 0 || ticket + 4 <= h->call_seq) return VADB_OK;      // nothing enqueued / long since overwritten
+  if (ticket >= h->call_seq) return fail(h, VADB_E_INVALID, "unknown ticket");
+  DeviceGuard dg(h->device);
+  CU_TRY(h, cudaEventSynchronize(h->ev_call[ticket & 3]));
   return VADB_OK;
 }
 

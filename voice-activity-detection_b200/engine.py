@@ -52,6 +52,19 @@ _DTYPES = {"fp32": _cabi.VADB_F32, "f32": _cabi.VADB_F32, "float32": _cabi.VADB_
            "bf16": _cabi.VADB_BF16, "bfloat16": _cabi.VADB_BF16}
 
 
+class HostTicket:
+    """Handle of one asynchronous host call (VadEngine.forward_async)."""
+
+    def __init__(self, engine, ticket, prob, logp, keep_alive):
+        self._engine, self._ticket, self._prob, self._logp, self._keep = engine, ticket, prob, logp, keep_alive
+
+    def wait(self):
+        rc = self._engine._lib.vadb_host_wait(self._engine._h, self._ticket)
+        _cabi.check(self._engine._lib, self._engine._h, rc, "vadb_host_wait")
+        self._keep = None
+        return self._prob, self._logp
+
+
 class VadEngine:
     """Owns a vadb_handle.  ``compute_dtype``: "fp32" (<=1e-3 parity path) or "bf16"."""
 
@@ -72,6 +85,7 @@ class VadEngine:
         rc = self._lib.vadb_create(C.byref(self._h), C.byref(self._cfg), self.device.index)
         _cabi.check(self._lib, None, rc, "vadb_create")
         self.weight_count = int(self._lib.vadb_weight_count(C.byref(self._cfg)))
+        self._async_out, self._async_n = {}, 0      # pinned output rings of forward_async, per shape
 
     # -- lifecycle ---------------------------------------------------------------------------
     def close(self):
@@ -166,6 +180,37 @@ class VadEngine:
             C.c_void_p(logp.data_ptr()) if want_logp and logp.numel() else None)
         _cabi.check(self._lib, self._h, rc, "vadb_forward_host")
         return prob, logp
+
+    def forward_async(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None,
+                      want_logp: bool = False, want_prob: bool = True) -> "HostTicket":
+        """Streaming form of the host call: x [B,T,F] fp32 in PINNED host memory; H2D, forward and D2H are
+        only enqueued, so the upload of the next batch overlaps the compute of this one.  Returns a
+        ticket whose ``wait()`` yields (prob, logp) pinned CPU tensors; the output buffers are a ring of
+        four per shape: a result is valid until four further calls."""
+        if x.is_cuda or not x.is_pinned() or x.dtype != torch.float32 or not x.is_contiguous():
+            raise ValueError("forward_async needs a contiguous fp32 tensor in pinned host memory")
+        if x.dim() != 3 or x.shape[2] != self.feature_size:
+            raise ValueError(f"expected [B,T,{self.feature_size}] features, got {tuple(x.shape)}")
+        B, T, _ = x.shape
+        key = (B, T, want_logp, want_prob)
+        ring = self._async_out.setdefault(key, [])
+        slot = self._async_n % 4
+        self._async_n += 1
+        while len(ring) <= slot:
+            ring.append((torch.empty((B, T), dtype=torch.float32).pin_memory() if want_prob else None,
+                         torch.empty((B, T, 2), dtype=torch.float32).pin_memory() if want_logp else None))
+        prob, logp = ring[slot]
+        ln_ptr, keep = None, None
+        if lengths is not None:
+            keep = lengths.to(device="cpu", dtype=torch.int32).contiguous()
+            ln_ptr = C.c_void_p(keep.data_ptr())
+        ticket = C.c_long(-1)
+        rc = self._lib.vadb_forward_host_async(
+            self._h, C.c_void_p(x.data_ptr()), ln_ptr, B, T,
+            C.c_void_p(prob.data_ptr()) if want_prob and prob.numel() else None,
+            C.c_void_p(logp.data_ptr()) if want_logp and logp.numel() else None, C.byref(ticket))
+        _cabi.check(self._lib, self._h, rc, "vadb_forward_host_async")
+        return HostTicket(self, ticket.value, prob, logp, (x, keep))
 
     def predict_probabilities(self, feature, half: int, jump: int):
         """feature [L,F] (numpy / CPU tensor -> host call; CUDA tensor -> device call).
