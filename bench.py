@@ -2,19 +2,23 @@
 """bench.py -- audio frames/s of the Self-Attentive VAD forward path on B200.
 
     python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own forward on host cores
+    python bench.py --config 5 [--gpus N]                    # BASELINE configs[4]: mixed-length batch, masks
+    python bench.py --config 4                               # BASELINE configs[3]: T=8192, B=64
 
 One "step" = one forward pass (front-end -> 3 encoder layers -> classifier) over one batch of
-synthetic log-mel clips.  Workload = BASELINE.json configs[1]: 256 clips x T=512 frames x F=64
-mel per GPU, bf16 tensor-core compute (weak scaling: N GPUs -> N x 256 clips, config 3 at N=8).
+synthetic log-mel clips.  Default workload = BASELINE.json configs[1]: 256 clips x T=512 frames x F=64
+mel per GPU, bf16 tensor-core compute (weak scaling: N GPUs -> N x 256 clips, configs[2] at N=8).
 Prints ONE JSON line (rank 0).  Keys: see the build contract; additionally
   roofline      attention kernel (the graded kernel) vs the measured HBM peak
-  cpu_baseline  the oracle port of the reference forward timed on this box's host cores
+  cpu_baseline  the reference forward (oracle/_ref when present, else the oracle port) on this box's host cores
   e2e           same metric through the public API with HOST tensors (H2D + D2H inside the timing)
+  secondary     configs[3] and configs[4] on this GPU (N=1 runs), rank_outputs_identical (N>1 runs)
 """
 import argparse
 import json
 import os
+import random
 import subprocess
 import sys
 import threading
@@ -31,6 +35,7 @@ B_PER_GPU, T, F, D, L = 256, 512, 64, 128, 3
 CPU_SAMPLE_B = 16          # clips per CPU-baseline forward (scores [B,1,T,T] x3 must fit RAM)
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 FALLBACK_BF16_TFLOPS = 1590.0
+LONG_RUN_S = 0.35          # the contract's K timed steps last ~10 ms; a second, longer loop carries the clock samples
 
 
 def measured_peaks():
@@ -55,7 +60,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -78,9 +83,10 @@ class ClockSampler:
         except Exception:
             pass
         sm, mx, reasons = [], None, set()
-        rows = [r for (ts, r) in self.rows if t_begin is None or (t_begin - 0.05 <= ts <= t_end + 0.15)]
+        rows = [r for (ts, r) in self.rows if t_begin is None or (t_begin <= ts <= t_end)]
+        window = "timed loops"
         if not rows:
-            rows = [r for (_, r) in self.rows]
+            rows, window = [r for (_, r) in self.rows], "whole run (no sample fell inside the timed loops)"
         for r in rows:
             try:
                 sm.append(float(r[0]))
@@ -92,10 +98,33 @@ class ClockSampler:
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
-def best_cpu_threads(st, x, O):
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own forward
+# ------------------------------------------------------------------------------------------------
+def reference_forward():
+    """-> (fn(x[B,T,F]) -> log-probs, kind, description).  kind "reference": the UNMODIFIED reference
+    modules placed in oracle/_ref by oracle/build_ref.py; "port": the oracle restatement (same op
+    sequence, pinned to the real modules at 2e-6) when oracle/_ref did not travel."""
+    from oracle import vad_oracle as O
+    from oracle.build_ref import import_reference_model
+    st = O.make_state(0, F, L, D)
+    M = import_reference_model()
+    if M is not None:
+        m = M(F, L, D, 0.5)
+        m.load_state_dict(st)
+        m.eval()
+
+        def fwd(x):
+            with torch.no_grad():
+                return m(features=x)
+        return fwd, "reference", "unmodified reference SelfAttentiveVAD (oracle/_ref), torch CPU fp32"
+    return (lambda x: O.forward_logp(st, x)), "port", "torch CPU oracle port with the reference's op sequence"
+
+
+def best_cpu_threads(fwd, x):
     """torch's CPU kernels do not scale to every core of a big host (the reference's own
     ``set_num_threads(os.cpu_count())`` recipe is ~50x SLOWER than 16 threads on a 128-core box),
     so give the CPU arm its best case: one short probe per candidate thread count."""
@@ -104,9 +133,9 @@ def best_cpu_threads(st, x, O):
     best, best_t = cands[0], float("inf")
     for c in cands:
         torch.set_num_threads(c)
-        O.forward_logp(st, x[:2])
+        fwd(x[:2])
         t0 = time.perf_counter()
-        O.forward_logp(st, x)
+        fwd(x)
         dt = time.perf_counter() - t0
         if dt < best_t:
             best, best_t = c, dt
@@ -115,46 +144,43 @@ def best_cpu_threads(st, x, O):
     return best
 
 
-def cpu_forward_rate(threads=None, budget_s=12.0, min_iters=3, warm=2):
-    """frames/s of the oracle port (reference algorithm, torch CPU fp32, same op sequence) on
-    the host cores; bounded sample: CPU_SAMPLE_B clips of T frames per forward."""
+def cpu_forward_rate(budget_s=12.0, min_iters=3, warm=2):
+    """frames/s of the reference forward on the host cores; bounded sample: CPU_SAMPLE_B clips of T frames."""
     from oracle import vad_oracle as O
-    st = O.make_state(0, F, L, D)
+    fwd, kind, what = reference_forward()
     x = O.make_input(1, CPU_SAMPLE_B, T, F)
-    if threads is None:
-        threads = best_cpu_threads(st, x, O)
+    threads = best_cpu_threads(fwd, x)
     torch.set_num_threads(threads)
     for _ in range(warm):
-        O.forward_logp(st, x)
+        fwd(x)
     times = []
     t_start = time.perf_counter()
     while len(times) < min_iters or (time.perf_counter() - t_start < budget_s and len(times) < 200):
         t0 = time.perf_counter()
-        O.forward_logp(st, x)
+        fwd(x)
         times.append(time.perf_counter() - t0)
     med = float(np.median(times))
-    return CPU_SAMPLE_B * T / med, med, len(times), threads
+    return CPU_SAMPLE_B * T / med, med, len(times), threads, kind, what
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU forward (oracle port: the reference is PyTorch code
-    that cannot travel to the GPU box; the port keeps its exact op sequence) on all host cores."""
+    """--impl reference: the reference's CPU forward on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import vad_oracle as O
-    st = O.make_state(0, F, L, D)
+    fwd, kind, what = reference_forward()
     x = O.make_input(1, CPU_SAMPLE_B, T, F)
-    torch.set_num_threads(best_cpu_threads(st, x, O))
+    torch.set_num_threads(best_cpu_threads(fwd, x))
     for _ in range(max(args.warmup, 1)):
-        O.forward_logp(st, x)
+        fwd(x)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.forward_logp(st, x)
+        fwd(x)
     dt = time.perf_counter() - t0
     value = args.steps * CPU_SAMPLE_B * T / dt
     sample = (f"{CPU_SAMPLE_B} clips x T={T} x F={F} per step (bounded sample of the "
-              f"{B_PER_GPU}-clip workload; fp32 oracle port of the reference forward)")
+              f"{B_PER_GPU}-clip workload); {what}")
     line = {
         "impl": "reference", "metric": "audio frames/sec (T=512,F=64)", "value": value,
         "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -163,11 +189,19 @@ def run_reference(args):
         "config": {"workload": f"batch={B_PER_GPU} clips T={T} F={F} (reference CPU forward, sampled)",
                    "sample_clips_per_step": CPU_SAMPLE_B},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(),
-                         "host_cores": os.cpu_count(), "kind": "port", "sample": sample},
+                         "host_cores": os.cpu_count(), "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def config5_lengths(n_clips, seed=0):
+    rnd = random.Random(seed)
+    return [rnd.choice((128, 512, 2048)) for _ in range(n_clips)]
 
 
 def main():
@@ -177,7 +211,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
+                    help="BASELINE.json configs index + 1: 2 = B=256,T=512 (headline); 4 = B=64,T=8192; 5 = mixed lengths")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -187,7 +224,7 @@ def main():
     import torch.distributed as dist
     from vad_b200 import synthetic as S                     # random-init weights (product side; the oracle is
                                                             # only imported by the cpu_baseline / reference legs)
-    from vad_b200.distributed import load_engine_from_broadcast
+    from vad_b200.distributed import balanced_assignment, load_engine_from_broadcast
     from vad_b200.engine import VadEngine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -210,17 +247,6 @@ def main():
     # ---- model: random-init weights of the named architecture; ONE broadcast at load ----
     eng = VadEngine(F, L, D, args.dtype, dev)
     load_engine_from_broadcast(eng, S.random_state(0, F, L, D) if rank == 0 else None, src=0)
-    eng.reserve(B_PER_GPU, T)
-
-    # ---- synthetic inputs: N_ROT distinct batches (> L2) rotated between iterations ----
-    N_ROT = 6
-    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
-    in_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    host_batches = [(torch.randn(B_PER_GPU, T, F, generator=g) * 2.0 - 3.0).pin_memory()
-                    for _ in range(2)]
-    dev_batches = [(torch.randn(B_PER_GPU, T, F, generator=g) * 2.0 - 3.0).to(dev).to(in_dtype)
-                   for _ in range(N_ROT)]
-    rot_bytes = sum(b.numel() * b.element_size() for b in dev_batches)
 
     def barrier():
         if world > 1:
@@ -241,141 +267,313 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    # ---- every rank holds the right weights: one fixed seeded batch, outputs compared bit for bit ----
+    rank_check = None
+    if world > 1:
+        xc = S.random_features(999, 8, T, F).to(dev)
+        pc, _ = eng.forward(xc, want_logp=False)
+        bits = pc.view(torch.int32).to(torch.int64)
+        sig = torch.stack([bits.sum(), (bits * torch.arange(1, bits.numel() + 1, device=dev).view_as(bits) % 1000003).sum()])
+        sigs = [torch.zeros_like(sig) for _ in range(world)]
+        dist.all_gather(sigs, sig)
+        rank_check = bool(all(torch.equal(s, sigs[0]) for s in sigs))
+        del xc, pc
+
+    in_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    sampler = ClockSampler(local_rank)
+    hbm_peak, tf_peak, peak_src = measured_peaks()
+
+    # =========================================================================================
+    if args.config == 5:
+        # BASELINE configs[4]: mixed-length batch (T in {128,512,2048}), padding masks, 64 clips per GPU,
+        # clips assigned to ranks by balanced sum of T^2 (vad_b200.distributed.balanced_assignment)
+        lengths_all = config5_lengths(64 * n_gpus)
+        mine = balanced_assignment(lengths_all, n_gpus)[rank]
+        lens = [lengths_all[i] for i in mine]
+        Tm = max(lens)
+        g = torch.Generator(device="cpu").manual_seed(4321)
+        x_all = torch.randn(len(lengths_all), 1, F, generator=g)          # per-clip offset: clips differ across ranks
+        xs = []
+        for r_ in range(3):
+            x = torch.randn(len(lens), Tm, F, generator=torch.Generator().manual_seed(100 * rank + r_)) * 2.0 - 3.0
+            x = x + 0.1 * x_all[mine]
+            for b, n in enumerate(lens):
+                x[b, n:] = 0.0
+            xs.append(x.to(dev).to(in_dtype))
+        ln = torch.tensor(lens, dtype=torch.int32, device=dev)
+        eng.reserve(len(lens), Tm)
+        if rank == 0:
+            sampler.start()
+        for i in range(args.warmup):
+            eng.forward(xs[i % 3], ln, want_logp=False)
+        launches0 = eng.launch_count
+        t_begin = sampler.mark()
+        ms_total = timed(lambda i: eng.forward(xs[i % 3], ln, want_logp=False), args.steps)
+        launches = eng.launch_count - launches0
+        long_steps = max(args.steps, int(LONG_RUN_S * 1e3 / max(ms_total / args.steps, 1e-3)))
+        ms_long = timed(lambda i: eng.forward(xs[i % 3], ln, want_logp=False), long_steps)
+        t_end = sampler.mark()
+        clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+        valid = torch.tensor([float(sum(lens))], device=dev)
+        if world > 1:
+            dist.all_reduce(valid)
+        valid = float(valid.item())
+        # fp32 vs bf16 tolerance sweep over VALID frames, on the device (both paths of this library)
+        other = "fp32" if args.dtype == "bf16" else "bf16"
+        eng2 = VadEngine(F, L, D, other, dev)
+        load_engine_from_broadcast(eng2, S.random_state(0, F, L, D) if rank == 0 else None, src=0, via="torch")
+        pa, _ = eng.forward(xs[0], ln, want_logp=False)
+        pb, _ = eng2.forward(xs[0].float(), ln, want_logp=False)
+        m = torch.arange(Tm, device=dev)[None, :] < ln[:, None]
+        dp = (pa - pb).abs()[m]
+        stats = torch.stack([dp.max(), dp.sum(), m.sum().float()])
+        if world > 1:
+            mx = stats[:1].clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(stats)
+            stats[0] = mx[0]
+        if rank == 0:
+            ms_per_step = ms_total / args.steps
+            line = {
+                "metric": "valid audio frames/sec (mixed T in {128,512,2048}, F=64)", "value": valid / (ms_per_step * 1e-3),
+                "unit": "frames/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": f"BASELINE configs[4]: {64 * n_gpus} clips, T_i = random.Random(0).choice((128,512,2048)), "
+                                       f"key-padding masks, {n_gpus} GPU(s), clips assigned by balanced sum of T^2",
+                           "valid_frames": valid, "padded_T_rank0": Tm, "clips_rank0": len(lens),
+                           "l2": "inputs rotated over 3 batches; intermediates exceed L2"},
+                "long_run": {"steps": long_steps, "ms_per_step": ms_long / long_steps},
+                "tolerance_sweep": {"compared": f"{args.dtype} vs {other} compute, same inputs, valid frames only",
+                                    "max_abs_dP": float(stats[0]), "mean_abs_dP": float(stats[1] / stats[2])},
+                "rank_outputs_identical": rank_check, "weights_load_path": getattr(eng, "load_path", None),
+                "gpu_launches": int(launches), "clocks": clocks,
+            }
+            json_out.write(json.dumps(line) + "\n")
+            json_out.flush()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # =========================================================================================
+    Bq, Tq = (B_PER_GPU, T) if args.config == 2 else (64, 8192)
+    eng.reserve(Bq, Tq)
+
+    # ---- synthetic inputs: N_ROT distinct batches (> L2) rotated between iterations ----
+    N_ROT = 6 if args.config == 2 else 2
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    host_f32 = [(torch.randn(Bq, Tq, F, generator=g) * 2.0 - 3.0).pin_memory() for _ in range(2)]
+    host_bf16 = [h.to(torch.bfloat16).pin_memory() for h in host_f32]
+    dev_batches = [(torch.randn(Bq, Tq, F, generator=g) * 2.0 - 3.0).to(dev).to(in_dtype) for _ in range(N_ROT)]
+    rot_bytes = sum(b.numel() * b.element_size() for b in dev_batches)
+
     def step_dev(i):
         eng.forward(dev_batches[i % N_ROT], want_logp=False)
 
-    def step_e2e(i):
-        # public API with HOST tensors: pinned H2D of the inputs + D2H of the result inside the call
-        eng.forward(host_batches[i % 2], want_logp=False)
-
-    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     for i in range(args.warmup):
         step_dev(i)
     launches0 = eng.launch_count
     t_begin = sampler.mark()
-    ms_total = timed(step_dev, args.steps)
-    t_end = sampler.mark()
+    ms_total = timed(step_dev, args.steps)                         # the contract's EXACTLY K timed steps -> value
     launches = eng.launch_count - launches0
     ms_per_step = ms_total / args.steps
-    value = n_gpus * B_PER_GPU * T / (ms_per_step * 1e-3)
-    if rank == 0 and (t_end - t_begin) < 0.5:
-        # the timed region is shorter than nvidia-smi's sampling period: keep the same work
-        # running (untimed) until a few samples under load exist
-        t_more = time.time()
-        i = 0
-        while time.time() - t_more < 0.6:
-            step_dev(i); i += 1
-        torch.cuda.synchronize()
-        t_end = sampler.mark()
+    value = n_gpus * Bq * Tq / (ms_per_step * 1e-3)
+    # the same loop again, long enough (>= 0.35 s) for nvidia-smi to sample clocks under exactly this load
+    long_steps = max(args.steps, int(LONG_RUN_S * 1e3 / ms_per_step))
+    ms_long = timed(step_dev, long_steps)
+    t_end = sampler.mark()
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
 
-    # ---- e2e ----
-    # (a) blocking call per step: upload, forward and read-back of a step finish before the next starts
-    for i in range(3):
-        step_e2e(i)
-    e2e_steps = max(3, min(args.steps, 10))
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        step_e2e(i)
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_sync_value = n_gpus * B_PER_GPU * T * e2e_steps / float(e2e_s.item())
-    # (b) streaming call (VadEngine.forward_async -> vadb_forward_host_async): the same per-step work --
-    # pinned H2D of that step's inputs, forward, D2H of its probabilities, the result read on the host --
-    # with the upload of step i+1 overlapping the compute of step i; every result is waited for and read
-    # inside the timed region
-    def run_stream(steps):
-        acc, pending = 0.0, None
+    # ---- e2e: public API with HOST tensors, every step uploads its inputs and reads its result back ----
+    def e2e_blocking(batches, steps):
+        for i in range(2):
+            eng.forward(batches[i % 2], want_logp=False)
+        barrier()
+        t0 = time.perf_counter()
         for i in range(steps):
-            tk = eng.forward_async(host_batches[i % 2])
-            if pending is not None:
-                acc += float(pending.wait()[0][0, 0])
-            pending = tk
-        acc += float(pending.wait()[0][0, 0])
-        return acc
-    run_stream(4)
-    stream_steps = max(6, min(args.steps, 20))
-    barrier()
-    t0 = time.perf_counter()
-    run_stream(stream_steps)
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = n_gpus * B_PER_GPU * T * stream_steps / float(e2e_s.item())
-    e2e_steps = stream_steps
+            eng.forward(batches[i % 2], want_logp=False)
+        torch.cuda.synchronize()
+        s = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(s, op=dist.ReduceOp.MAX)
+        return n_gpus * Bq * Tq * steps / float(s.item())
+
+    def e2e_stream(batches, steps):
+        # streaming call (VadEngine.forward_async -> vadb_forward_host_async): pinned H2D of that step's
+        # inputs, forward, D2H of its probabilities, the result read on the host; the upload of step i+1
+        # overlaps the compute of step i; every result is waited for and read inside the timed region
+        def run(n):
+            acc, pending = 0.0, None
+            for i in range(n):
+                tk = eng.forward_async(batches[i % 2])
+                if pending is not None:
+                    acc += float(pending.wait()[0][0, 0])
+                pending = tk
+            acc += float(pending.wait()[0][0, 0])
+            return acc
+        run(4)
+        barrier()
+        t0 = time.perf_counter()
+        run(steps)
+        torch.cuda.synchronize()
+        s = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(s, op=dist.ReduceOp.MAX)
+        return n_gpus * Bq * Tq * steps / float(s.item())
+
+    e2e_steps = max(6, min(args.steps, 20))
+    e2e_block_f32 = e2e_blocking(host_f32, max(3, min(args.steps, 10)))
+    e2e_stream_f32 = e2e_stream(host_f32, e2e_steps)
+    e2e_stream_bf16 = e2e_stream(host_bf16, e2e_steps) if args.dtype == "bf16" else None
+    # H2D ceiling of this box with all ranks uploading concurrently (pinned, same sizes, copies only)
+    def h2d_ceiling(src_batches):
+        dst = torch.empty_like(src_batches[0], device=dev)
+        for i in range(3):
+            dst.copy_(src_batches[i % 2], non_blocking=True)
+        reps = 20
+        ms = timed(lambda i: dst.copy_(src_batches[i % 2], non_blocking=True), reps) / reps
+        return src_batches[0].numel() * src_batches[0].element_size() / (ms * 1e-3) / 1e9
+    h2d_gbs_f32 = h2d_ceiling(host_f32)
+    h2d_gbs_bf16 = h2d_ceiling(host_bf16)
+    if args.dtype == "bf16":
+        e2e_value, e2e_in_bytes, e2e_in = e2e_stream_bf16, Bq * Tq * F * 2, "bf16"
+        e2e_ceiling = n_gpus * Bq * Tq / (e2e_in_bytes / (h2d_gbs_bf16 * 1e9))
+    else:
+        e2e_value, e2e_in_bytes, e2e_in = e2e_stream_f32, Bq * Tq * F * 4, "fp32"
+        e2e_ceiling = n_gpus * Bq * Tq / (e2e_in_bytes / (h2d_gbs_f32 * 1e9))
 
     # ---- roofline of the attention kernel (the graded kernel), timed alone with CUDA events ----
-    hbm_peak, tf_peak, peak_src = measured_peaks()
     roofline = None
     try:
         qkv_sets = []
         gg = torch.Generator(device="cpu").manual_seed(7)
-        act_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-        for _ in range(3):      # 3 x (q,k,v,o) = 3 x 134 MB (bf16) > L2
-            qkv_sets.append(tuple(torch.randn(B_PER_GPU, T, D, generator=gg).to(dev).to(act_dtype)
-                                  for _ in range(3)))
+        n_sets = 3 if args.config == 2 else 2
+        for _ in range(n_sets):      # 3 x (q,k,v,o) = 3 x 134 MB (bf16) > L2
+            qkv_sets.append(tuple(torch.randn(Bq, Tq, D, generator=gg).to(dev).to(in_dtype) for _ in range(3)))
         for i in range(3):
-            eng.attention(*qkv_sets[i % 3])
-        attn_iters = 20
-        ms_attn = timed(lambda i: eng.attention(*qkv_sets[i % 3]), attn_iters) / attn_iters
+            eng.attention(*qkv_sets[i % n_sets])
+        attn_iters = 20 if args.config == 2 else 5
+        ms_attn = timed(lambda i: eng.attention(*qkv_sets[i % n_sets]), attn_iters) / attn_iters
         esz = 2 if args.dtype == "bf16" else 4
-        alg_bytes = 4 * B_PER_GPU * T * D * esz            # read Q,K,V + write O once
-        alg_flops = 4 * B_PER_GPU * T * T * D               # QK^T + PV
+        alg_bytes = 4 * Bq * Tq * D * esz                  # read Q,K,V + write O once
+        alg_flops = 4 * Bq * Tq * Tq * D                    # QK^T + PV
         achieved = alg_bytes / (ms_attn * 1e-3) / 1e9
-        traffic = None
-        try:    # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (per launch)
-            with open(os.path.join(ROOT, "profiles", "r1_attn_ncu_summary.json")) as f:
-                traffic = json.load(f)["final"]["traffic_bytes_per_launch"]
-        except Exception:
-            pass
-        roofline = {"kernel": "attention (per layer-call, B=256,T=512,d=128)", "bound": "hbm",
+        traffic, traffic_src = None, None
+        for name in ("r2_attn_ncu_summary.json", "r1_attn_ncu_summary.json"):
+            try:    # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (per launch)
+                with open(os.path.join(ROOT, "profiles", name)) as f:
+                    traffic = json.load(f)["final"]["traffic_bytes_per_launch"]
+                traffic_src = "profiles/" + name
+                break
+            except Exception:
+                continue
+        roofline = {"kernel": f"attention (per layer-call, B={Bq},T={Tq},d=128)", "bound": "hbm",
                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": traffic, "peak_source": peak_src, "us_per_launch": ms_attn * 1e3,
-                    "algorithmic_bytes": alg_bytes,
+                    "traffic": traffic if args.config == 2 else None, "traffic_source": traffic_src,
+                    "peak_source": peak_src, "us_per_launch": ms_attn * 1e3, "algorithmic_bytes": alg_bytes,
                     "tensor": {"achieved": alg_flops / (ms_attn * 1e-3) / 1e12, "peak": tf_peak,
                                "unit": "TFLOP/s", "frac": alg_flops / (ms_attn * 1e-3) / 1e12 / tf_peak}}
         del qkv_sets
     except Exception as e:  # pragma: no cover
         roofline = {"error": str(e)}
 
-    # ---- CPU baseline (rank 0, N=1 only): oracle port on the host cores, bounded sample ----
+    # ---- secondary (rank 0, N=1): BASELINE configs[3] and configs[4] on this GPU, driver-run ----
+    secondary = None
+    if rank == 0 and n_gpus == 1 and args.config == 2 and args.dtype == "bf16" and not args.no_secondary:
+        secondary = {}
+        try:
+            del dev_batches
+            torch.cuda.empty_cache()
+
+            def tms(fn, iters, warm=2):
+                for _ in range(warm):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / iters
+            gs = torch.Generator(device="cpu").manual_seed(44)
+            x4 = (torch.randn(64, 8192, F, generator=gs) * 2.0 - 3.0).to(dev).to(torch.bfloat16)
+            ms4 = tms(lambda: eng.forward(x4, want_logp=False), 5)
+            fl4 = L * 4 * 64 * 8192 * 8192 * D
+            secondary["config4_B64_T8192_bf16"] = {
+                "ms_per_forward": ms4, "frames_per_s": 64 * 8192 / ms4 * 1e3,
+                "attention_tflops": fl4 / (ms4 * 1e-3) / 1e12,
+                "attention_tflops_frac_of_measured_bf16_peak": fl4 / (ms4 * 1e-3) / 1e12 / tf_peak,
+                "note": "whole forward timed; FLOPs counted are the attention QK^T+PV only (T=8192 is compute-bound)"}
+            del x4
+            lens = config5_lengths(64)
+            x5 = torch.randn(64, 2048, F, generator=gs) * 2.0 - 3.0
+            for b, n in enumerate(lens):
+                x5[b, n:] = 0.0
+            x5 = x5.to(dev)
+            ln5 = torch.tensor(lens, dtype=torch.int32, device=dev)
+            x5b = x5.to(torch.bfloat16)
+            ms5 = tms(lambda: eng.forward(x5b, ln5, want_logp=False), 10)
+            eng32 = VadEngine(F, L, D, "fp32", dev)
+            eng32.load_state_dict(S.random_state(0, F, L, D))
+            pa, _ = eng.forward(x5, ln5, want_logp=False)
+            pb, _ = eng32.forward(x5, ln5, want_logp=False)
+            m = torch.arange(2048, device=dev)[None, :] < ln5[:, None]
+            dp = (pa - pb).abs()[m]
+            secondary["config5_mixed_64clips_bf16"] = {
+                "ms_per_forward": ms5, "valid_frames": int(sum(lens)), "valid_frames_per_s": sum(lens) / ms5 * 1e3,
+                "config2_frames_per_s_for_comparison": value,
+                "fp32_vs_bf16_max_abs_dP_valid": float(dp.max()), "fp32_vs_bf16_mean_abs_dP_valid": float(dp.mean())}
+            eng32.close()
+            del x5, x5b, pa, pb
+        except Exception as e:  # pragma: no cover
+            secondary["error"] = repr(e)
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference forward on the host cores, bounded sample ----
     cpu_baseline = None
-    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
-        rate, med, iters, cores = cpu_forward_rate()
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline and args.config == 2:
+        rate, med, iters, cores, kind, what = cpu_forward_rate()
         cpu_baseline = {"value": rate, "unit": "frames/s", "cores": cores,
-                        "host_cores": os.cpu_count(), "kind": "port",
+                        "host_cores": os.cpu_count(), "kind": kind,
                         "sample": f"{iters} forwards of {CPU_SAMPLE_B} clips x T={T} x F={F} fp32 "
-                                  f"(median {med * 1e3:.1f} ms); torch CPU oracle port with the "
-                                  "reference's op sequence"}
+                                  f"(median {med * 1e3:.1f} ms); {what}"}
 
     if rank == 0:
+        cfg_name = "BASELINE configs[1]" if args.config == 2 else "BASELINE configs[3] (long context)"
         line = {
-            "metric": "audio frames/sec (T=512,F=64)", "value": value, "unit": "frames/s",
+            "metric": f"audio frames/sec (T={Tq},F={F})", "value": value, "unit": "frames/s",
             "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"batch={B_PER_GPU} clips/GPU x T={T} x F={F}, SelfAttentiveVAD(L={L},d={D}), "
-                                   f"{args.dtype} compute (BASELINE configs[1]; x{n_gpus} GPUs batch-sharded)",
-                       "global_batch": n_gpus * B_PER_GPU, "seq_len": T, "parallelism": f"dp{n_gpus}",
+            "config": {"workload": f"batch={Bq} clips/GPU x T={Tq} x F={F}, SelfAttentiveVAD(L={L},d={D}), "
+                                   f"{args.dtype} compute ({cfg_name}; x{n_gpus} GPUs batch-sharded)",
+                       "global_batch": n_gpus * Bq, "seq_len": Tq, "parallelism": f"dp{n_gpus}",
                        "l2": f"inputs rotated over {N_ROT} batches ({rot_bytes / 1e6:.0f} MB) + "
-                             "intermediates (~0.5 GB/step) exceed the 126 MB L2",
-                       "weights": "random init (seed 0), one NCCL broadcast at load"},
+                             "intermediates (> 1 GB of HBM traffic per step) exceed the 126 MB L2",
+                       "weights": "random init (seed 0), one NCCL broadcast at load "
+                                  f"({getattr(eng, 'load_path', 'single GPU: vadb_load_weights')})"},
+            "long_run": {"steps": long_steps, "ms_per_step": ms_long / long_steps,
+                         "value": n_gpus * Bq * Tq / (ms_long / long_steps * 1e-3),
+                         "note": "same loop repeated for >= 0.35 s: the clock samples cover both loops"},
             "e2e": {"value": e2e_value, "unit": "frames/s",
-                    "h2d_bytes_per_step": B_PER_GPU * T * F * 4, "d2h_bytes_per_step": B_PER_GPU * T * 4,
-                    "steps": e2e_steps,
+                    "h2d_bytes_per_step": e2e_in_bytes, "d2h_bytes_per_step": Bq * Tq * 4,
+                    "steps": e2e_steps, "host_input_dtype": e2e_in,
                     "api": "VadEngine.forward_async(pinned cpu tensor) -> vadb_forward_host_async, one ticket "
                            "waited per step (upload of step i+1 overlaps compute of step i; every result read "
                            "inside the timed region)",
-                    "blocking_call_value": e2e_sync_value,
-                    "blocking_call_api": "VadEngine.forward(cpu_tensor) -> vadb_forward_host"},
+                    "fp32_host_features_value": e2e_stream_f32, "fp32_host_features_h2d_bytes_per_step": Bq * Tq * F * 4,
+                    "blocking_call_value": e2e_block_f32,
+                    "blocking_call_api": "VadEngine.forward(fp32 cpu_tensor) -> vadb_forward_host",
+                    "h2d_ceiling_gbs": h2d_gbs_bf16 if e2e_in == "bf16" else h2d_gbs_f32,
+                    "h2d_ceiling_gbs_fp32_buffers": h2d_gbs_f32,
+                    "h2d_ceiling_note": "pinned H2D copies alone, same buffers, all ranks concurrently, max over ranks",
+                    "upload_bound_value": e2e_ceiling,
+                    "frac_of_min_upload_or_compute": e2e_value / min(e2e_ceiling, value)},
             "gpu_launches": int(launches),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "secondary": secondary, "rank_outputs_identical": rank_check,
         }
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()

@@ -73,6 +73,15 @@ size_t vadb_weight_count(const vadb_config* cfg);
  * kernel-side copies (bf16 / fused QKV / classifier).  Synchronises `stream` before return. */
 int vadb_load_weights(vadb_handle* h, const float* blob, size_t count, int on_device, void* stream);
 
+/* Multi-GPU load: ONE NCCL broadcast of the packed blob from rank `root` (which has called
+ * vadb_load_weights) into every other rank's handle, followed by the same derivation of the kernel-side
+ * copies.  This is the only collective of the whole path (there is none in steady state); it replaces the
+ * reference's training-time nn.DataParallel replication (vad/training/trainer.py:115-116) for inference.
+ *  nccl_comm  an ncclComm_t (passed as void*) whose ranks each own one handle on their own device
+ * NCCL is resolved at run time from the calling process (dlsym, else dlopen("libnccl.so.2")): the
+ * library has no link-time dependency on it.  Collective: every rank of the communicator must call it. */
+int vadb_broadcast_weights(vadb_handle* h, void* nccl_comm, int root, void* stream);
+
 /* Pre-size the workspace (and positional-encoding table) for calls up to B clips x T frames. */
 int vadb_reserve(vadb_handle* h, int B, int T);
 
@@ -90,17 +99,23 @@ int vadb_forward(vadb_handle* h, const void* x, int x_dtype, const int32_t* leng
  * pinned buffers, copies H2D, runs the forward and copies the results D2H, on its own
  * stream, and returns when the outputs are in host memory.  This is the end-to-end
  * entry the reference-facing wrapper uses for numpy / CPU-tensor inputs
- * (vad/predictor.py:223 .to(device), :247 .cpu()). */
-int vadb_forward_host(vadb_handle* h, const float* x, const int32_t* lengths, int B, int T,
+ * (vad/predictor.py:223 .to(device), :247 .cpu()).
+ *  x        host [B,T,F], x_dtype VADB_F32 or VADB_BF16 (bf16 features halve the upload; the bf16
+ *           compute mode rounds the features to bf16/tf32 operands anyway)
+ *  logp     any alignment is accepted (B*T may be odd) */
+int vadb_forward_host(vadb_handle* h, const void* x, int x_dtype, const int32_t* lengths, int B, int T,
                       float* prob, float* logp);
 
 /* Asynchronous form for streaming many batches: everything (H2D, forward, D2H) is only enqueued on the
  * library's streams and the call returns at once, so the upload of the next batch overlaps the compute of
  * this one (throughput = max(upload, compute) instead of their pipelined sum).  x, prob and logp must be
- * PINNED host buffers and stay valid/untouched until vadb_host_wait(h, ticket) has returned; at most four
- * calls may be outstanding.  Same reference interface as vadb_forward_host, called in a loop over batches
- * (vad/predictor.py:182-258 iterates chunks of windows the same way, synchronously). */
-int vadb_forward_host_async(vadb_handle* h, const float* x, const int32_t* lengths, int B, int T,
+ * PINNED host buffers and stay valid/untouched until vadb_host_wait(h, ticket) has returned.  At most four
+ * calls may be outstanding: a fifth call before the oldest ticket was waited for fails with VADB_E_STATE
+ * (nothing is enqueued).  Calls complete in ticket order; vadb_host_wait never reports success without
+ * having synchronised on the ticket's (or a later) completion event.  Same reference interface as
+ * vadb_forward_host, called in a loop over batches (vad/predictor.py:182-258 iterates chunks of windows
+ * the same way, synchronously). */
+int vadb_forward_host_async(vadb_handle* h, const void* x, int x_dtype, const int32_t* lengths, int B, int T,
                             float* prob, float* logp, long* ticket);
 int vadb_host_wait(vadb_handle* h, long ticket);
 

@@ -57,3 +57,14 @@ def valid_mask(shape_BT, lengths):
 def prob_from_logp(logp):
     e = np.exp(logp - logp.max(axis=-1, keepdims=True))
     return (e / e.sum(axis=-1, keepdims=True))[..., 1]
+
+
+WEATHER_WAV = os.path.join(GOLDEN_DIR, "When_the_Weather_Is_Fine_12_4.wav")
+
+
+def weather_wav():
+    """The reference's tests/test_predict.py fixture: (AudioData, checkpoint config dict, golden [L,7])."""
+    import json
+    from vad_b200.data_models import AudioData
+    z = np.load(os.path.join(GOLDEN_DIR, "weather_wav_golden.npz"))
+    return AudioData.load(WEATHER_WAV), json.loads(str(z["config_json"])), z["probs"]

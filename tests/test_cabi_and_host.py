@@ -273,9 +273,33 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
     assert d["metric"] == "audio frames/sec (T=512,F=64)" and d["higher_is_better"] is True
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # the unmodified reference modules when oracle/_ref travelled with the snapshot, else the oracle port
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "vad", "models", "self_attention.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     # a non-zero rank exits quietly
     r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1"],
                         capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_oracle_ref_recipe_and_agreement_with_port():
+    """oracle/_ref (the reference's own model files, placed by oracle/build_ref.py; git-ignored) is what
+    `bench.py --impl reference` times when present: it must be the reference class, not the repository's
+    compatibility shim, and agree with the oracle port on the bench's sample."""
+    import subprocess
+    import sys
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "vad", "models", "self_attention.py")):
+        pytest.skip("oracle/_ref not built (no /root/reference at build time)")
+    code = (
+        "import sys, torch; sys.path.insert(0, %r)\n"
+        "from oracle.build_ref import import_reference_model\n"
+        "from oracle import vad_oracle as O\n"
+        "M = import_reference_model(); assert M is not None and issubclass(M, torch.nn.Module)\n"
+        "st = O.make_state(0, 64, 3, 128); m = M(64, 3, 128, 0.5); m.load_state_dict(st); m.eval()\n"
+        "x = O.make_input(1, 2, 128, 64)\n"
+        "with torch.no_grad(): got = m(features=x)\n"
+        "print(float((got - O.forward_logp(st, x)).abs().max()))\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert float(r.stdout.strip().splitlines()[-1]) <= 2e-6

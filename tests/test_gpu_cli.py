@@ -88,3 +88,44 @@ def test_cli_predict_and_evaluate(ckpt, tmp_path):
     assert r.exit_code == 0, r.output
     total = json.loads(open(res).readline())
     assert 0.0 <= total["auc"] <= 1.0 and "boosted_eer" in total
+
+
+# ----------------------------------------------------------------------------------------------
+# The reference's own end-to-end fixtures (its tests/test_predict.py:12-30): the real wav and the real
+# test checkpoint's weights, goldens from the unmodified reference model (tests/golden/make_wav_golden.py)
+# ----------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def real_ckpt(tmp_path_factory):
+    from tests.golden_util import sample_checkpoint_state, weather_wav
+    _, cfg, _ = weather_wav()
+    d = tmp_path_factory.mktemp("realck")
+    torch.save({"state_dict": sample_checkpoint_state(), "epoch": 0, "global_step": 2, "config": cfg,
+                "metrics": {"val_auc": np.float64(0.585)}}, d / "sample.checkpoint")
+    return d / "sample.checkpoint"
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_reference_wav_predict_probabilities_vs_reference_golden(real_ckpt, dtype):
+    from tests.golden_util import weather_wav
+    from vad.predictor import VADFromScratchPredictor
+    audio, _, want = weather_wav()
+    pred = VADFromScratchPredictor.from_checkpoint(real_ckpt, torch.device("cuda"), compute_dtype=dtype)
+    probs = pred.predict_probabilities(audio)             # PCM -> log-mel -> windows -> model -> boost, on the device
+    assert probs.shape == want.shape == (1022, 7)
+    err = np.abs(probs - want).max()
+    print(f"reference wav, {dtype}: max|dP| = {err:.3e}")
+    assert err <= (1e-3 if dtype == "fp32" else 1e-2)
+    np.testing.assert_array_equal(probs[want == 0.5], 0.5)
+
+
+def test_reference_wav_cli_predict(real_ckpt, tmp_path):
+    """Mirror of the reference's tests/test_predict.py: exit code 0 and at least one activity."""
+    from typer.testing import CliRunner
+    from main import app
+    from tests.golden_util import WEATHER_WAV
+    from vad_b200.data_models import VoiceActivity
+    out = tmp_path / "va.json"
+    r = CliRunner().invoke(app, ["predict", WEATHER_WAV, str(real_ckpt), "--output-path", str(out)])
+    assert r.exit_code == 0, r.output
+    va = VoiceActivity.load(out)
+    assert len(va.activities) > 0

@@ -73,3 +73,17 @@ def test_positional_encoding_values():
 def test_mask_from_lengths():
     m = O.mask_from_lengths(torch.tensor([1, 3]), 4)
     assert m.tolist() == [[False, True, True, True], [False, False, False, True]]
+
+
+def test_reference_wav_fixture_matches_reference():
+    """The reference's own end-to-end fixture (its tests/test_predict.py wav + test checkpoint): the oracle's
+    predictor on this repository's host log-mel features against the UNMODIFIED reference model run through
+    the literal transcription of vad/predictor.py:169-258 (tests/golden/make_wav_golden.py)."""
+    from tests.golden_util import weather_wav
+    audio, cfg, want = weather_wav()
+    from vad_b200.features import FeatureExtractor
+    feat = FeatureExtractor(cfg["feature_extractor"]).extract_with_postprocessing(audio)
+    assert feat.shape == (1022, 80)
+    got = O.predict_probabilities(sample_checkpoint_state(), feat, 19, 9)
+    assert got.shape == want.shape == (1022, 7)
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)

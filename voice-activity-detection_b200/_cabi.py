@@ -13,7 +13,7 @@ SYMBOLS = (
     "vadb_reserve", "vadb_forward", "vadb_forward_host", "vadb_predict_probabilities",
     "vadb_predict_probabilities_host", "vadb_attention", "vadb_positional_table",
     "vadb_launch_count", "vadb_version", "vadb_logmel_frames", "vadb_logmel", "vadb_logmel_tables",
-    "vadb_predict_audio_host", "vadb_forward_host_async", "vadb_host_wait",
+    "vadb_predict_audio_host", "vadb_forward_host_async", "vadb_host_wait", "vadb_broadcast_weights",
 )
 
 
@@ -47,11 +47,13 @@ def load_library():
     lib.vadb_weight_count.restype = sz
     lib.vadb_load_weights.argtypes = [vp, vp, sz, i32, vp]
     lib.vadb_load_weights.restype = i32
+    lib.vadb_broadcast_weights.argtypes = [vp, vp, i32, vp]
+    lib.vadb_broadcast_weights.restype = i32
     lib.vadb_reserve.argtypes = [vp, i32, i32]
     lib.vadb_reserve.restype = i32
     lib.vadb_forward.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
     lib.vadb_forward.restype = i32
-    lib.vadb_forward_host.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    lib.vadb_forward_host.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp]
     lib.vadb_forward_host.restype = i32
     lib.vadb_predict_probabilities.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     lib.vadb_predict_probabilities.restype = i32
@@ -71,7 +73,7 @@ def load_library():
     lib.vadb_logmel_tables.restype = i32
     lib.vadb_predict_audio_host.argtypes = [vp, vp, C.c_long, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.vadb_predict_audio_host.restype = i32
-    lib.vadb_forward_host_async.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.POINTER(C.c_long)]
+    lib.vadb_forward_host_async.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, C.POINTER(C.c_long)]
     lib.vadb_forward_host_async.restype = i32
     lib.vadb_host_wait.argtypes = [vp, C.c_long]
     lib.vadb_host_wait.restype = i32

@@ -40,8 +40,11 @@ class Config(dict):
 def _safe_globals():
     # the reference checkpoint pickles numpy scalars inside "metrics"; torch >= 2.6 defaults to
     # weights_only=True and needs these allow-listed
-    return [(np._core.multiarray.scalar, "numpy.core.multiarray.scalar"),     # numpy < 2 pickles
-            np._core.multiarray.scalar, np.dtype,
+    # numpy >= 1.26 exposes the implementation module as np._core, older releases only as np.core
+    core = getattr(np, "_core", None) or np.core
+    scalar = core.multiarray.scalar
+    return [(scalar, "numpy.core.multiarray.scalar"),     # pickles written by numpy < 2
+            scalar, np.dtype,
             _codecs.encode, type(np.dtype("float64")), type(np.dtype("float32")),
             type(np.dtype("int64"))]
 

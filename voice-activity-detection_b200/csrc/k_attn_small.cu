@@ -187,15 +187,9 @@ attn_small_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K, const 
 bool attn_small_supported(int T) { return T >= 1 && T <= SMALL_T_MAX; }
 
 cudaError_t launch_attn_small(const bf16* q, const bf16* k, const bf16* v, bf16* o, const int32_t* lengths,
-                              int B, int T, cudaStream_t s) {
+                              int B, int T, int num_sms, cudaStream_t s) {
   if (B <= 0 || T <= 0) return cudaSuccess;
   if (!attn_small_supported(T)) return cudaErrorInvalidValue;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
   const int n_pairs = (B + 1) / 2;
   const long want = ((long)n_pairs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
   const long cap = (long)num_sms * 16;            // 64 warps per SM; each warp then loops over its pairs

@@ -666,13 +666,7 @@ CUresult make_tmap_bt128(CUtensorMap* map, const void* base, int B, int T, int b
 }
 
 cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o, const int32_t* lengths,
-                           int B, int T, cudaStream_t s, std::string* err) {
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+                           int B, int T, int num_sms, cudaStream_t s, std::string* err) {
   if (B <= 0 || T <= 0) return cudaSuccess;
   CUtensorMap tq, tk, tv, to;
   CUresult r;

@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(256) classifier_kernel(const float* __restrict
                                                          const float* __restrict__ wc,
                                                          const float* __restrict__ bc, int M,
                                                          float* __restrict__ prob,
-                                                         float* __restrict__ logp) {
+                                                         float* __restrict__ logp, int tiled) {
   const int lane = threadIdx.x & 31;
   const long warp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) classifier_kernel(const float* __restrict
     float4 xr[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      xr[u] = (row0 + u < M) ? __ldcg(reinterpret_cast<const float4*>(h + (row0 + u) * D) + lane)
+      xr[u] = (row0 + u < M) ? __ldcg(reinterpret_cast<const float4*>(h) + h_quad_index(row0 + u, lane, tiled))
                              : make_float4(0.f, 0.f, 0.f, 0.f);
     float st[4];
 #pragma unroll
@@ -83,12 +83,12 @@ __global__ void __launch_bounds__(256) classifier_kernel(const float* __restrict
 }  // namespace
 
 cudaError_t launch_classifier(const float* h, const float* g, const float* b, const float* wc,
-                              const float* bc, int M, float* prob, float* logp, cudaStream_t s) {
+                              const float* bc, int M, float* prob, float* logp, int tiled, cudaStream_t s) {
   if (M <= 0) return cudaSuccess;
   const int warps_per_block = 8;
   long blocks = ((long)M + 4 * warps_per_block - 1) / (4 * warps_per_block);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  { cudaError_t e = launch_k(classifier_kernel, (unsigned)blocks, warps_per_block * 32, 0, s, h, g, b, wc, bc, M, prob, logp); if (e != cudaSuccess) return e; }
+  { cudaError_t e = launch_k(classifier_kernel, (unsigned)blocks, warps_per_block * 32, 0, s, h, g, b, wc, bc, M, prob, logp, tiled); if (e != cudaSuccess) return e; }
   return cudaGetLastError();
 }
 

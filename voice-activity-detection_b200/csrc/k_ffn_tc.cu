@@ -60,6 +60,7 @@ struct FfnParams {
   const float* cls_bias; // [2]
   float* prob;           // [M] or nullptr
   float* logp;           // [M,2] or nullptr
+  int logp_vec;          // logp is 8-byte aligned: one float2 store per row
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
@@ -330,7 +331,10 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__
           const float a1 = z1 + xs[256 + row * 2] + __ldg(p.cls_bias + 1);
           const float mx = fmaxf(a0, a1);
           const float lse = mx + log1pf(expf(-fabsf(a1 - a0)));        // log_softmax([a0, a1]), stable
-          if (p.logp) *reinterpret_cast<float2*>(p.logp + grow * 2) = make_float2(a0 - lse, a1 - lse);
+          if (p.logp) {
+            if (p.logp_vec) *reinterpret_cast<float2*>(p.logp + grow * 2) = make_float2(a0 - lse, a1 - lse);
+            else { p.logp[grow * 2] = a0 - lse; p.logp[grow * 2 + 1] = a1 - lse; }
+          }
           if (p.prob) p.prob[grow] = 1.0f / (1.0f + expf(a0 - a1));     // softmax(logp)[1]
         }
       } else if (p.emit_g) {
@@ -418,6 +422,7 @@ cudaError_t launch_ffn_tc(const FfnTcArgs& a, int num_sms, cudaStream_t s, std::
   p.h_out = a.h; p.emit_out = a.emit_out;
   p.cls_g = a.cls_ln_g; p.cls_b = a.cls_ln_b; p.cls_w = a.cls_w; p.cls_bias = a.cls_bias;
   p.prob = a.prob; p.logp = a.logp;
+  p.logp_vec = (reinterpret_cast<uintptr_t>(a.logp) % 8) == 0;
   if (p.cls_g && (!p.cls_b || !p.cls_w || !p.cls_bias)) return cudaErrorInvalidValue;
   static thread_local int attr_dev = -1;
   int dev = 0;

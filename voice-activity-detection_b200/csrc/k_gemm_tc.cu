@@ -65,6 +65,7 @@ struct GemmTcParams {
                             // K counts 64-float stages (K/128 of them), element coordinates are halved
   int out_f32;              // 1: fp32 output [M, N]; 0: bf16
   int out_split;            // bf16 outputs: columns [j*128, j*128+128) -> out map j when split (q,k,v)
+  int out_tiled;            // fp32 N == 128 output in the tiled residual layout: direct coalesced stores from registers
   // fp32 output with N == 128 only: additionally emit LayerNorm(out_row) in bf16 through tm_o1 -- the A
   // operand of the NEXT kernel (pre-LN of the following sublayer, transformer.py:235-236), so that kernel
   // is fed by TMA instead of register-staged producer warps
@@ -446,7 +447,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         // phase 2: stage and store
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
-          if (p.out_f32) {
+          if (p.out_f32 && p.out_tiled) {
+            // tiled residual layout [tile][32 column quads][128 rows][4 floats]: a warp's 32 rows of one column
+            // quad are 512 contiguous bytes
+            float4* dst = reinterpret_cast<float4*>(p.out_ptr[0]) + (size_t)tile * 4096 + (size_t)(hsel * 16 + cb * 8) * 128 + row;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              dst[c * 128] = make_float4(__uint_as_float(v[cb][4 * c]), __uint_as_float(v[cb][4 * c + 1]),
+                                         __uint_as_float(v[cb][4 * c + 2]), __uint_as_float(v[cb][4 * c + 3]));
+          } else if (p.out_f32) {
             // one store unit = 32 fp32 columns (128 B per row)
             const uint32_t so = next_slab();
 #pragma unroll
@@ -557,6 +566,8 @@ cudaError_t launch_gemm_tc(const GemmTcArgs& a, int num_sms, cudaStream_t s, std
   p.bias = a.bias; p.relu = a.relu; p.residual = a.residual; p.res_mod = a.res_mod;
   p.out_f32 = a.out_f32; p.out_split = a.out[1] != nullptr && !a.emit_ln_g;
   p.emit_g = a.emit_ln_g; p.emit_b = a.emit_ln_b;
+  p.out_tiled = a.out_tiled;
+  if (a.out_tiled && !(a.out_f32 && a.N == 128)) return bad("tiled output needs fp32 N == 128");
   // residual tiles by TMA: the residual stream itself, or the positional-encoding table when a 128-row tile
   // never wraps around it (res_mod % 128 == 0: row (tile * 128) % res_mod onwards is contiguous)
   p.res_tma = (a.residual && (a.res_mod == 0 || a.res_mod % 128 == 0) && !p.prod && a.out_f32) ? 1 : 0;

@@ -46,7 +46,7 @@ __global__ void boost_kernel(const float* __restrict__ prob_nW, int L, int half,
 __global__ void __launch_bounds__(256)
 window_gather_ln_kernel(const float* __restrict__ proj, const float* __restrict__ pe, float* __restrict__ out_h,
                         bf16* __restrict__ out_ln, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
-                        long n_rows, int W, int half, int jump) {
+                        long n_rows, int W, int half, int jump, int tiled) {
   const int lane = threadIdx.x & 31;
   const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long n_warps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -61,7 +61,7 @@ window_gather_ln_kernel(const float* __restrict__ proj, const float* __restrict_
     float4 v = *(reinterpret_cast<const float4*>(proj + src * D) + lane);     // written by the previous kernel
     const float4 e = __ldg(reinterpret_cast<const float4*>(pe + (long)k * D) + lane);
     v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
-    __stcs(reinterpret_cast<float4*>(out_h + m * D) + lane, v);
+    reinterpret_cast<float4*>(out_h)[h_quad_index(m, lane, tiled)] = v;
     float sum = (v.x + v.y) + (v.z + v.w);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -77,6 +77,39 @@ window_gather_ln_kernel(const float* __restrict__ proj, const float* __restrict_
     pk.x = *reinterpret_cast<uint32_t*>(&lo);
     pk.y = *reinterpret_cast<uint32_t*>(&hi);
     __stcs(reinterpret_cast<uint2*>(out_ln + m * D) + lane, pk);
+  }
+}
+
+// Row-major fp32 residual rows -> tiled layout + LayerNorm(row) in bf16: used when the front end ran on the
+// CUDA-core fallback (feature sizes the tensor-core front end does not take) in bf16 mode.  One warp per row.
+__global__ void __launch_bounds__(256)
+retile_ln_kernel(const float* __restrict__ h_rows, float* __restrict__ h_tiled, bf16* __restrict__ out_ln,
+                 const float* __restrict__ ln_g, const float* __restrict__ ln_b, long n_rows) {
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long n_warps = ((long)gridDim.x * blockDim.x) >> 5;
+  const float4 gam = __ldg(reinterpret_cast<const float4*>(ln_g) + lane);
+  const float4 bet = __ldg(reinterpret_cast<const float4*>(ln_b) + lane);
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
+  for (long m = warp; m < n_rows; m += n_warps) {
+    const float4 v = *(reinterpret_cast<const float4*>(h_rows + m * D) + lane);
+    reinterpret_cast<float4*>(h_tiled)[h_quad_index(m, lane, 1)] = v;
+    float sum = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / D);
+    const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+    float sq = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.0f / D) + LN_EPS);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(dx * rstd * gam.x + bet.x, dy * rstd * gam.y + bet.y);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(dz * rstd * gam.z + bet.z, dw * rstd * gam.w + bet.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *(reinterpret_cast<uint2*>(out_ln + m * D) + lane) = pk;
   }
 }
 
@@ -114,11 +147,19 @@ cudaError_t launch_pad_rows_bf16(const float* in, bf16* out, int rows, int cols,
 
 cudaError_t launch_window_gather_ln(const float* proj, const float* pe, float* out_h, bf16* out_ln,
                                     const float* ln_g, const float* ln_b, long n_rows, int W, int half,
-                                    int jump, cudaStream_t s) {
+                                    int jump, int tiled, cudaStream_t s) {
   if (n_rows <= 0) return cudaSuccess;
   long blocks = (n_rows + 7) / 8;                 // 8 warps (rows) per block per pass
   if (blocks > 148 * 8) blocks = 148 * 8;         // a multiple of the SM count; warps then stride over rows
-  return launch_k(window_gather_ln_kernel, (unsigned)blocks, 256, 0, s, proj, pe, out_h, out_ln, ln_g, ln_b, n_rows, W, half, jump);
+  return launch_k(window_gather_ln_kernel, (unsigned)blocks, 256, 0, s, proj, pe, out_h, out_ln, ln_g, ln_b, n_rows, W, half, jump, tiled);
+}
+
+cudaError_t launch_retile_ln(const float* h_rows, float* h_tiled, bf16* out_ln, const float* ln_g,
+                             const float* ln_b, long n_rows, cudaStream_t s) {
+  if (n_rows <= 0) return cudaSuccess;
+  long blocks = (n_rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  return launch_k(retile_ln_kernel, (unsigned)blocks, 256, 0, s, h_rows, h_tiled, out_ln, ln_g, ln_b, n_rows);
 }
 
 cudaError_t launch_boost(const float* prob_nW, int L, int half, int jump, int W, float* probs_LW,

@@ -1,5 +1,6 @@
 // C ABI of libvadb200.so (see include/vadb200.h): handle, weights, workspace and the
 // orchestration of the forward pass / predictor window path on a caller-provided stream.
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -58,6 +59,7 @@ struct vadb_handle {
   bf16* w1_bf = nullptr;     // [L][512*128]
   bf16* w2_bf = nullptr;     // [L][128*512]
   bf16* win_bf = nullptr;    // [128, 128] front-end weight, columns >= F zero (tensor-core front end)
+  unsigned char* wtail = nullptr;   // [L] packed weight blocks of the fused layer-tail kernel (k_tail_tc.cu)
 
   float* pe = nullptr;       // [pe_T, 128] = PE / sqrt(d)
   int pe_T = 0;
@@ -77,6 +79,7 @@ struct vadb_handle {
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   cudaEvent_t ev_call[4] = {nullptr, nullptr, nullptr, nullptr};   // completion of the last four asynchronous host calls
   long call_seq = 0, chunk_seq = 0;
+  long waited_upto = -1;     // every asynchronous host call with ticket <= waited_upto is known to have completed
   size_t last_chunk_in = 0;
   void* pin_in = nullptr; size_t pin_in_bytes = 0;
   void* pin_out = nullptr; size_t pin_out_bytes = 0;
@@ -121,6 +124,13 @@ struct DeviceGuard {
 
 bool is_bf16_mode(const vadb_handle* h) { return h->cfg.compute_dtype == VADB_BF16; }
 
+// bf16 mode: out-projection + FFN + next layer's Q/K/V (or the classifier) in one kernel per layer, residual
+// stream in the tiled layout (k_tail_tc.cu).  VADB_FUSE_TAIL=0 keeps the round-1 kernel sequence (A/B runs).
+bool fuse_tail(const vadb_handle* h) {
+  static const bool on = !(getenv("VADB_FUSE_TAIL") && atoi(getenv("VADB_FUSE_TAIL")) == 0);
+  return on && is_bf16_mode(h);
+}
+
 template <typename T>
 void free_dev(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
 
@@ -157,7 +167,7 @@ int ensure_workspace(vadb_handle* h, size_t frames) {
   free_dev(h->ws_hid); free_dev(h->ws_prob); free_dev(h->ws_aln);
   h->cap_frames = 0;
   const size_t act = is_bf16_mode(h) ? sizeof(bf16) : sizeof(float);
-  CU_TRY(h, cudaMalloc(&h->ws_h, cap * D * sizeof(float)));
+  CU_TRY(h, cudaMalloc(&h->ws_h, ((cap + 127) / 128 * 128) * D * sizeof(float)));   // whole 128-row tiles (tiled layout)
   CU_TRY(h, cudaMalloc(&h->ws_q, cap * D * act));
   CU_TRY(h, cudaMalloc(&h->ws_k, cap * D * act));
   CU_TRY(h, cudaMalloc(&h->ws_v, cap * D * act));
@@ -196,12 +206,12 @@ int attention(vadb_handle* h, const void* q, const void* k, const void* v, void*
   static const bool small_ok = !(getenv("VADB_ATTN_SMALL") && atoi(getenv("VADB_ATTN_SMALL")) == 0);
   if (dtype == VADB_BF16 && small_ok && attn_small_supported(T)) {
     // the reference Predictor's 7-frame windows: a 128-row tcgen05 tile would be 94 % padding
-    cudaError_t e = launch_attn_small((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, lengths, B, T, s);
+    cudaError_t e = launch_attn_small((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, lengths, B, T, h->num_sms, s);
     if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("attn_small: ") + cudaGetErrorString(e));
   } else if (dtype == VADB_BF16) {
     std::string err;
     cudaError_t e = launch_attn_tc((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, lengths,
-                                   B, T, s, &err);
+                                   B, T, h->num_sms, s, &err);
     if (e != cudaSuccess)
       return fail(h, VADB_E_CUDA, std::string("attn_tc: ") + cudaGetErrorString(e) + " " + err);
   } else {
@@ -220,6 +230,44 @@ int run_encoder(vadb_handle* h, const int32_t* lengths, int Bc, int T, float* pr
   const float* w = h->w32;
   const bool bf = is_bf16_mode(h);
   static const bool fuse_cls = !(getenv("VADB_FUSE_CLS") && atoi(getenv("VADB_FUSE_CLS")) == 0);
+  if (fuse_tail(h)) {
+    // bf16 mode, fused: [Q/K/V of layer 0] then per layer [attention, layer tail]; the tail kernel of layer l
+    // also produces q,k,v of layer l+1, the last one the probabilities (2 + 2L launches per forward)
+    const int L = h->cfg.num_layers;
+    int rc;
+    {
+      const LayerOffsets& lo = h->lay.layers[0];
+      GemmTcArgs g = {};
+      g.M = M; g.N = 3 * D; g.K = D; g.w_bf16 = h->wqkv_bf;
+      if (h->aln_valid) g.a_bf16 = h->ws_aln;
+      else return fail(h, VADB_E_STATE, "internal: LayerNorm operand of layer 0 missing");
+      (void)lo;
+      g.bias = h->bqkv;
+      g.out[0] = h->ws_q; g.out[1] = h->ws_k; g.out[2] = h->ws_v;
+      if ((rc = gemm_tc(h, g, s))) return rc;
+    }
+    for (int l = 0; l < L; ++l) {
+      const LayerOffsets& lo = h->lay.layers[l];
+      if ((rc = attention(h, h->ws_q, h->ws_k, h->ws_v, h->ws_o, VADB_BF16, lengths, Bc, T, s))) return rc;
+      TailTcArgs t = {};
+      t.M = M; t.wpack = h->wtail + (size_t)l * tail_pack_bytes(); t.o = (const bf16*)h->ws_o; t.h = h->ws_h;
+      t.bo = w + lo.bo; t.b1 = w + lo.b1; t.b2 = w + lo.b2; t.ln2_g = w + lo.ln2_g; t.ln2_b = w + lo.ln2_b;
+      if (l + 1 < L) {
+        const LayerOffsets& ln = h->lay.layers[l + 1];
+        t.ln1n_g = w + ln.ln1_g; t.ln1n_b = w + ln.ln1_b; t.bqkv = h->bqkv + (size_t)(l + 1) * 3 * D;
+        t.q = (bf16*)h->ws_q; t.k = (bf16*)h->ws_k; t.v = (bf16*)h->ws_v;
+      } else {
+        t.cls_ln_g = w + h->lay.lnf_g; t.cls_ln_b = w + h->lay.lnf_b; t.cls_w = w + h->lay.wc; t.cls_bias = w + h->lay.bc;
+        t.prob = prob; t.logp = logp;
+      }
+      std::string err;
+      cudaError_t e = launch_tail_tc(t, h->num_sms, s, &err);
+      if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("tail_tc: ") + cudaGetErrorString(e) + " " + err);
+      h->launches++;
+    }
+    h->aln_valid = false;
+    return VADB_OK;
+  }
   for (int l = 0; l < h->cfg.num_layers; ++l) {
     const LayerOffsets& lo = h->lay.layers[l];
     int rc;
@@ -304,7 +352,7 @@ int run_encoder(vadb_handle* h, const int32_t* lengths, int Bc, int T, float* pr
   }
   if (bf && fuse_cls) return VADB_OK;
   cudaError_t e = launch_classifier(h->ws_h, w + h->lay.lnf_g, w + h->lay.lnf_b, w + h->lay.wc,
-                                    w + h->lay.bc, M, prob, logp, s);
+                                    w + h->lay.bc, M, prob, logp, 0, s);
   if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("classifier: ") + cudaGetErrorString(e));
   h->launches++;
   return VADB_OK;
@@ -337,6 +385,7 @@ int front_end(vadb_handle* h, const void* x, int x_is_bf16, int M, int pe_T, int
     // also emit LN1 of layer 0 in bf16: the A operand of the first Q/K/V GEMM
     g.out[1] = h->ws_aln;
     g.emit_ln_g = h->w32 + h->lay.layers[0].ln1_g; g.emit_ln_b = h->w32 + h->lay.layers[0].ln1_b;
+    g.out_tiled = fuse_tail(h) ? 1 : 0;
     h->aln_valid = true;
     return gemm_tc(h, g, s);
   }
@@ -347,6 +396,19 @@ int front_end(vadb_handle* h, const void* x, int x_is_bf16, int M, int pe_T, int
   g.M = M; g.N = D; g.K = F; g.pe = h->pe; g.pe_T = pe_T;
   g.win_W = win_W; g.win_half = win_half; g.win_jump = win_jump;
   g.out[0] = h->ws_h; g.out_split = D;
+  if (fuse_tail(h)) {
+    // CUDA-core front end (feature sizes the tensor-core front end does not take) feeding the fused bf16
+    // layers: rows go to the (otherwise unused) hidden workspace, then into the tiled layout + LN1 of layer 0
+    g.out[0] = h->ws_hid;
+    int rc = gemm(h, g, s);
+    if (rc) return rc;
+    cudaError_t e = launch_retile_ln((const float*)h->ws_hid, h->ws_h, h->ws_aln, h->w32 + h->lay.layers[0].ln1_g,
+                                     h->w32 + h->lay.layers[0].ln1_b, M, s);
+    if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("retile: ") + cudaGetErrorString(e));
+    h->launches++;
+    h->aln_valid = true;
+    return VADB_OK;
+  }
   return gemm(h, g, s);
 }
 
@@ -438,7 +500,7 @@ void vadb_destroy(vadb_handle* h) {
   DeviceGuard dg(h->device);
   cudaDeviceSynchronize();
   free_dev(h->w32); free_dev(h->wqkv); free_dev(h->bqkv);
-  free_dev(h->wqkv_bf); free_dev(h->wo_bf); free_dev(h->w1_bf); free_dev(h->w2_bf); free_dev(h->win_bf);
+  free_dev(h->wqkv_bf); free_dev(h->wo_bf); free_dev(h->w1_bf); free_dev(h->w2_bf); free_dev(h->win_bf); free_dev(h->wtail);
   free_dev(h->pe);
   free_dev(h->ws_h); free_dev(h->ws_q); free_dev(h->ws_k); free_dev(h->ws_v); free_dev(h->ws_o);
   free_dev(h->ws_hid); free_dev(h->ws_prob); free_dev(h->ws_aln);
@@ -466,28 +528,24 @@ void vadb_destroy(vadb_handle* h) {
   delete h;
 }
 
-int vadb_load_weights(vadb_handle* h, const float* blob, size_t count, int on_device, void* stream) {
-  if (!h || !blob) return VADB_E_INVALID;
-  if (count != h->lay.total) {
-    char buf[160];
-    snprintf(buf, sizeof buf, "weight blob has %zu floats, config needs %zu", count, h->lay.total);
-    return fail(h, VADB_E_INVALID, buf);
-  }
-  DeviceGuard dg(h->device);
-  cudaStream_t s = (cudaStream_t)stream;
+static int alloc_weights(vadb_handle* h) {
+  if (h->w32) return VADB_OK;
   const int L = h->cfg.num_layers;
-  if (!h->w32) {
-    CU_TRY(h, cudaMalloc(&h->w32, count * sizeof(float)));
-    CU_TRY(h, cudaMalloc(&h->wqkv, (size_t)L * 3 * D * D * sizeof(float)));
-    CU_TRY(h, cudaMalloc(&h->bqkv, (size_t)L * 3 * D * sizeof(float)));
-    CU_TRY(h, cudaMalloc(&h->wqkv_bf, (size_t)L * 3 * D * D * sizeof(bf16)));
-    CU_TRY(h, cudaMalloc(&h->wo_bf, (size_t)L * D * D * sizeof(bf16)));
-    CU_TRY(h, cudaMalloc(&h->w1_bf, (size_t)L * DFF * D * sizeof(bf16)));
-    CU_TRY(h, cudaMalloc(&h->w2_bf, (size_t)L * D * DFF * sizeof(bf16)));
-    CU_TRY(h, cudaMalloc(&h->win_bf, (size_t)D * D * sizeof(bf16)));
-  }
-  CU_TRY(h, cudaMemcpyAsync(h->w32, blob, count * sizeof(float),
-                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  CU_TRY(h, cudaMalloc(&h->w32, h->lay.total * sizeof(float)));
+  CU_TRY(h, cudaMalloc(&h->wqkv, (size_t)L * 3 * D * D * sizeof(float)));
+  CU_TRY(h, cudaMalloc(&h->bqkv, (size_t)L * 3 * D * sizeof(float)));
+  CU_TRY(h, cudaMalloc(&h->wqkv_bf, (size_t)L * 3 * D * D * sizeof(bf16)));
+  CU_TRY(h, cudaMalloc(&h->wo_bf, (size_t)L * D * D * sizeof(bf16)));
+  CU_TRY(h, cudaMalloc(&h->w1_bf, (size_t)L * DFF * D * sizeof(bf16)));
+  CU_TRY(h, cudaMalloc(&h->w2_bf, (size_t)L * D * DFF * sizeof(bf16)));
+  CU_TRY(h, cudaMalloc(&h->win_bf, (size_t)D * D * sizeof(bf16)));
+  CU_TRY(h, cudaMalloc(&h->wtail, (size_t)L * tail_pack_bytes()));
+  return VADB_OK;
+}
+
+// kernel-side copies of the packed blob in h->w32: fused Q|K|V rows, bf16 operands
+static int derive_weights(vadb_handle* h, cudaStream_t s) {
+  const int L = h->cfg.num_layers;
   if (h->cfg.feature_size <= D)
     CU_TRY(h, launch_pad_rows_bf16(h->w32 + h->lay.w_in, h->win_bf, D, h->cfg.feature_size, s));
   for (int l = 0; l < L; ++l) {
@@ -505,9 +563,64 @@ int vadb_load_weights(vadb_handle* h, const float* blob, size_t count, int on_de
     CU_TRY(h, launch_f32_to_bf16(h->w32 + lo.w1, h->w1_bf + (size_t)l * DFF * D, (size_t)DFF * D, s));
     CU_TRY(h, launch_f32_to_bf16(h->w32 + lo.w2, h->w2_bf + (size_t)l * D * DFF, (size_t)D * DFF, s));
   }
+  for (int l = 0; l < L; ++l) {      // fused layer tail: Wo, W1, W2 of layer l + the fused Q|K|V weight of layer l+1
+    const LayerOffsets& lo = h->lay.layers[l];
+    CU_TRY(h, launch_tail_pack(h->w32 + lo.wo, h->w32 + lo.w1, h->w32 + lo.w2,
+                               l + 1 < L ? h->wqkv + (size_t)(l + 1) * 3 * D * D : nullptr,
+                               h->wtail + (size_t)l * tail_pack_bytes(), s));
+  }
   CU_TRY(h, cudaStreamSynchronize(s));
   h->loaded = true;
   return VADB_OK;
+}
+
+int vadb_load_weights(vadb_handle* h, const float* blob, size_t count, int on_device, void* stream) {
+  if (!h || !blob) return VADB_E_INVALID;
+  if (count != h->lay.total) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "weight blob has %zu floats, config needs %zu", count, h->lay.total);
+    return fail(h, VADB_E_INVALID, buf);
+  }
+  DeviceGuard dg(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = alloc_weights(h);
+  if (rc) return rc;
+  CU_TRY(h, cudaMemcpyAsync(h->w32, blob, count * sizeof(float),
+                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  return derive_weights(h, s);
+}
+
+// NCCL is resolved at run time (the process that owns the communicator has it loaded already; otherwise
+// libnccl.so.2 is opened), so libvadb200.so carries no link-time dependency on it.
+int vadb_broadcast_weights(vadb_handle* h, void* nccl_comm, int root, void* stream) {
+  if (!h || !nccl_comm) return VADB_E_INVALID;
+  typedef int (*BcastFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  typedef int (*RankFn)(void*, int*);
+  static BcastFn bcast = nullptr;
+  static RankFn user_rank = nullptr;
+  if (!bcast) {
+    void* sym = dlsym(RTLD_DEFAULT, "ncclBroadcast");
+    void* lib = nullptr;
+    if (!sym && (lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL))) sym = dlsym(lib, "ncclBroadcast");
+    if (!sym) return fail(h, VADB_E_STATE, "ncclBroadcast not found: load NCCL (libnccl.so.2) into the process first");
+    void* sym2 = dlsym(RTLD_DEFAULT, "ncclCommUserRank");
+    if (!sym2 && lib) sym2 = dlsym(lib, "ncclCommUserRank");
+    if (!sym2) return fail(h, VADB_E_STATE, "ncclCommUserRank not found");
+    bcast = reinterpret_cast<BcastFn>(sym);
+    user_rank = reinterpret_cast<RankFn>(sym2);
+  }
+  int rank = -1;
+  if (user_rank(nccl_comm, &rank) != 0) return fail(h, VADB_E_INVALID, "ncclCommUserRank failed (bad communicator?)");
+  if (rank == root && !h->loaded) return fail(h, VADB_E_STATE, "the root rank must have loaded its weights (vadb_load_weights)");
+  DeviceGuard dg(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = alloc_weights(h);
+  if (rc) return rc;
+  const int nccl_float32 = 7;      // ncclFloat32 (nccl.h, stable since NCCL 2.0)
+  const int nr = bcast(h->w32, h->w32, h->lay.total, nccl_float32, root, nccl_comm, s);
+  if (nr != 0) return fail(h, VADB_E_CUDA, "ncclBroadcast failed with ncclResult " + std::to_string(nr));
+  if (rank == root) { CU_TRY(h, cudaStreamSynchronize(s)); return VADB_OK; }
+  return derive_weights(h, s);
 }
 
 int vadb_reserve(vadb_handle* h, int B, int T) {
@@ -555,25 +668,31 @@ int vadb_forward(vadb_handle* h, const void* x, int x_dtype, const int32_t* leng
 
 // Shared body of vadb_forward_host (ticket == nullptr: returns when the outputs are in host memory) and
 // vadb_forward_host_async (ticket != nullptr: everything is only enqueued; pinned buffers required).
-static int forward_host_impl(vadb_handle* h, const float* x, const int32_t* lengths, int B, int T,
+static int forward_host_impl(vadb_handle* h, const void* x, int x_dtype, const int32_t* lengths, int B, int T,
                              float* prob, float* logp, long* ticket) {
   int rc = check_ready(h);
   if (rc) return rc;
   if (!x || B < 0 || T < 0) return fail(h, VADB_E_INVALID, "bad forward arguments");
+  if (x_dtype != VADB_F32 && x_dtype != VADB_BF16) return fail(h, VADB_E_INVALID, "x_dtype must be f32 or bf16");
   if (ticket) *ticket = -1;
   if (B == 0 || T == 0) return VADB_OK;
+  // the completion events and the caller's pinned output buffers form a ring of four: a fifth call may
+  // only be enqueued once the oldest outstanding ticket has been waited for
+  if (ticket && h->call_seq - 4 > h->waited_upto)
+    return fail(h, VADB_E_STATE, "four asynchronous host calls are outstanding: vadb_host_wait on a ticket first");
   DeviceGuard dg(h->device);
   // Chunked two-stream pipeline: the H2D copy of clip chunk i+1 overlaps the forward of chunk i
   // (the reference does one blocking .to(device) per 1000-window chunk, vad/predictor.py:223).
   cudaStream_t s_copy = h->own_stream, s_comp = h->own_stream2;
   const int F = h->cfg.feature_size;
-  const size_t clip_in = (size_t)T * F * sizeof(float);
+  const size_t clip_in = (size_t)T * F * (x_dtype == VADB_BF16 ? sizeof(bf16) : sizeof(float));
   // >= 8 MB per chunk, at most 4 chunks: enough overlap, few (small, launch-bound) forward passes
   // (measured on B200, 33.5 MB of features: 1 chunk 1.25 ms, 2: 1.06, 3: 1.11, 4: 1.04, 6: 1.38)
   int C = (int)std::max<size_t>(1, ((size_t)8 << 20) / std::max<size_t>(clip_in, 1));
   C = std::max(C, (B + 3) / 4);
   C = std::min(C, B);
-  if (ticket) C = std::max(1, (B + 1) / 2);           // asynchronous calls overlap ACROSS calls: two chunks suffice
+  if (ticket) C = B;                                  // asynchronous calls overlap ACROSS calls (two device input slots): one chunk,
+                                                      // one full-size forward (two half-size forwards cost ~15 % more compute)
   if (const char* e = getenv("VADB_HOST_CHUNKS")) {    // tuning knob: force the number of chunks
     const int want = atoi(e);
     if (want >= 1) C = std::max(1, (B + want - 1) / want);
@@ -600,7 +719,7 @@ static int forward_host_impl(vadb_handle* h, const float* x, const int32_t* leng
   if (!in_pinned && (rc = ensure_bytes(h, &h->pin_in, &h->pin_in_bytes, 2 * chunk_in, true))) return rc;
   if (!out_pinned && (rc = ensure_bytes(h, &h->pin_out, &h->pin_out_bytes, n * 3 * sizeof(float), true))) return rc;
   if ((rc = ensure_bytes(h, &h->dev_in, &h->dev_in_bytes, 2 * chunk_in, false))) return rc;
-  if ((rc = ensure_bytes(h, &h->dev_out, &h->dev_out_bytes, n * 3 * sizeof(float), false))) return rc;
+  if ((rc = ensure_bytes(h, &h->dev_out, &h->dev_out_bytes, (n * 3 + 4) * sizeof(float), false))) return rc;
   if ((rc = ensure_pe(h, T))) return rc;
   if ((rc = ensure_workspace(h, (size_t)std::min(C, clips_per_pass(C, T)) * T))) return rc;
   int32_t* dlen = nullptr;
@@ -615,7 +734,7 @@ static int forward_host_impl(vadb_handle* h, const float* x, const int32_t* leng
     dlen = h->dev_len;
   }
   float* dprob = (float*)h->dev_out;
-  float* dlogp = dprob + n;
+  float* dlogp = dprob + ((n + 3) & ~(size_t)3);       // 16-byte aligned for any B*T (the fused classifier stores float2)
   float* hprob = out_pinned ? prob : (float*)h->pin_out;
   float* hlogp = out_pinned ? logp : (float*)h->pin_out + n;
   for (int i = 0; i < n_chunks; ++i) {
@@ -637,7 +756,7 @@ static int forward_host_impl(vadb_handle* h, const float* x, const int32_t* leng
     CU_TRY(h, cudaMemcpyAsync(dsti, src, bytes, cudaMemcpyHostToDevice, s_copy));
     CU_TRY(h, cudaEventRecord(h->ev_h2d[slot], s_copy));
     CU_TRY(h, cudaStreamWaitEvent(s_comp, h->ev_h2d[slot], 0));
-    if ((rc = vadb_forward(h, dsti, VADB_F32, dlen ? dlen + b0 : nullptr, Bc, T,
+    if ((rc = vadb_forward(h, dsti, x_dtype, dlen ? dlen + b0 : nullptr, Bc, T,
                            prob ? dprob + (size_t)b0 * T : nullptr,
                            logp ? dlogp + (size_t)b0 * T * 2 : nullptr, s_comp)))
       return rc;
@@ -655,6 +774,7 @@ static int forward_host_impl(vadb_handle* h, const float* x, const int32_t* leng
   }
   CU_TRY(h, cudaStreamSynchronize(s_comp));
   CU_TRY(h, cudaStreamSynchronize(s_copy));
+  h->waited_upto = h->call_seq - 1;       // earlier asynchronous calls ran on the same streams: all complete
   if (!out_pinned) {
     if (prob) memcpy(prob, hprob, n * sizeof(float));
     if (logp) memcpy(logp, hlogp, 2 * n * sizeof(float));
@@ -662,23 +782,30 @@ static int forward_host_impl(vadb_handle* h, const float* x, const int32_t* leng
   return VADB_OK;
 }
 
-int vadb_forward_host(vadb_handle* h, const float* x, const int32_t* lengths, int B, int T,
+int vadb_forward_host(vadb_handle* h, const void* x, int x_dtype, const int32_t* lengths, int B, int T,
                       float* prob, float* logp) {
-  return forward_host_impl(h, x, lengths, B, T, prob, logp, nullptr);
+  return forward_host_impl(h, x, x_dtype, lengths, B, T, prob, logp, nullptr);
 }
 
-int vadb_forward_host_async(vadb_handle* h, const float* x, const int32_t* lengths, int B, int T,
+int vadb_forward_host_async(vadb_handle* h, const void* x, int x_dtype, const int32_t* lengths, int B, int T,
                             float* prob, float* logp, long* ticket) {
   if (!ticket) return h ? fail(h, VADB_E_INVALID, "ticket must not be NULL") : VADB_E_INVALID;
-  return forward_host_impl(h, x, lengths, B, T, prob, logp, ticket);
+  return forward_host_impl(h, x, x_dtype, lengths, B, T, prob, logp, ticket);
 }
 
 int vadb_host_wait(vadb_handle* h, long ticket) {
   if (!h) return VADB_E_INVALID;
-  if (ticket < 0 || ticket + 4 <= h->call_seq) return VADB_OK;      // nothing enqueued / long since overwritten
+  if (ticket < 0) return VADB_OK;                                   // empty call: nothing was enqueued
   if (ticket >= h->call_seq) return fail(h, VADB_E_INVALID, "unknown ticket");
+  if (ticket <= h->waited_upto) return VADB_OK;                     // already known to be complete
   DeviceGuard dg(h->device);
-  CU_TRY(h, cudaEventSynchronize(h->ev_call[ticket & 3]));
+  // Calls complete in ticket order (one compute stream).  A ticket whose own event slot has been reused
+  // by a later call (it cannot be, given the bound in vadb_forward_host_async, but stay safe) waits for
+  // the NEWEST call instead -- never "success" without a synchronisation.
+  const bool slot_reused = ticket + 4 < h->call_seq;       // call ticket+4 (recorded when call_seq was ticket+4) took the slot
+  const long on = slot_reused ? h->call_seq - 1 : ticket;
+  CU_TRY(h, cudaEventSynchronize(h->ev_call[on & 3]));
+  if (on > h->waited_upto) h->waited_upto = on;
   return VADB_OK;
 }
 
@@ -726,7 +853,7 @@ int vadb_predict_probabilities(vadb_handle* h, const float* feat, int L, int hal
       if (ptg) {
         cudaError_t e = launch_window_gather_ln((const float*)h->win_proj + (size_t)c0 * D, h->pe, h->ws_h, h->ws_aln,
                                                 h->w32 + h->lay.layers[0].ln1_g, h->w32 + h->lay.layers[0].ln1_b,
-                                                (long)nc * W, W, half, jump, s);
+                                                (long)nc * W, W, half, jump, fuse_tail(h) ? 1 : 0, s);
         if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("window gather: ") + cudaGetErrorString(e));
         h->aln_valid = true;
         h->launches++;

@@ -29,6 +29,10 @@ typedef __nv_bfloat16 bf16;
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// float4 index of (row m, column quad c4) of the fp32 residual stream: tiled [tile][32 c4][128 rows] or row-major
+__device__ __forceinline__ size_t h_quad_index(long m, int c4, int tiled) {
+  return tiled ? (size_t)(m >> 7) * 4096 + (size_t)c4 * 128 + (size_t)(m & 127) : (size_t)m * 32 + (size_t)c4;
+}
 #endif
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
@@ -87,14 +91,14 @@ cudaError_t launch_attn_f32(const float* q, const float* k, const float* v, floa
 
 // bf16 tcgen05 attention (k_attn_tc.cu)
 cudaError_t launch_attn_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o,
-                           const int32_t* lengths, int B, int T, cudaStream_t s,
+                           const int32_t* lengths, int B, int T, int num_sms, cudaStream_t s,
                            std::string* err);
 
 // bf16 attention for T <= 8 (the 7-frame windows of the reference Predictor): one warp per pair of
 // windows on mma.sync, no shared memory (k_attn_small.cu)
 bool attn_small_supported(int T);
 cudaError_t launch_attn_small(const bf16* q, const bf16* k, const bf16* v, bf16* o,
-                              const int32_t* lengths, int B, int T, cudaStream_t s);
+                              const int32_t* lengths, int B, int T, int num_sms, cudaStream_t s);
 
 // tcgen05 GEMM for the per-frame Linears in bf16 mode (k_gemm_tc.cu)
 struct GemmTcArgs {
@@ -118,6 +122,9 @@ struct GemmTcArgs {
   // fp32 N == 128 outputs: also write LayerNorm(out_row) (gamma/beta of the NEXT sublayer) as bf16 to out[1]
   const float* emit_ln_g;
   const float* emit_ln_b;
+  // fp32 N == 128 output written in the TILED residual layout [tile][32 column quads][128 rows][4 floats]
+  // (what k_tail_tc.cu reads and writes) instead of row-major
+  int out_tiled;
 };
 cudaError_t launch_gemm_tc(const GemmTcArgs& a, int num_sms, cudaStream_t s, std::string* err);
 
@@ -144,9 +151,30 @@ struct FfnTcArgs {
 };
 cudaError_t launch_ffn_tc(const FfnTcArgs& a, int num_sms, cudaStream_t s, std::string* err);
 
-// final LayerNorm + classifier + sigmoid/log-softmax (k_classifier.cu)
+// fused layer tail: out-projection + residual + LN2 + FFN + residual + (LN1_next + Q/K/V of the next layer |
+// final LayerNorm + classifier) in one kernel (k_tail_tc.cu); h is the TILED fp32 residual stream, updated in place
+struct TailTcArgs {
+  int M;
+  const unsigned char* wpack;   // packed weight blocks of this layer (launch_tail_pack)
+  const bf16* o;                // [M,128] attention output
+  float* h;                     // tiled residual stream
+  const float* bo; const float* b1; const float* b2;
+  const float* ln2_g; const float* ln2_b;
+  // not the last layer: next layer's pre-LN, q|k|v biases [384] and the three outputs
+  const float* ln1n_g; const float* ln1n_b; const float* bqkv;
+  bf16* q; bf16* k; bf16* v;    // q == nullptr -> last layer: classifier epilogue
+  const float* cls_ln_g; const float* cls_ln_b; const float* cls_w; const float* cls_bias;
+  float* prob; float* logp;
+};
+size_t tail_pack_bytes();       // bytes of one layer's packed blocks
+// wqkv_next: fused [384,128] q|k|v weight of the next layer, nullptr for the last layer
+cudaError_t launch_tail_pack(const float* wo, const float* w1, const float* w2, const float* wqkv_next,
+                             unsigned char* dst, cudaStream_t s);
+cudaError_t launch_tail_tc(const TailTcArgs& a, int num_sms, cudaStream_t s, std::string* err);
+
+// final LayerNorm + classifier + sigmoid/log-softmax (k_classifier.cu); tiled: h in the tiled residual layout
 cudaError_t launch_classifier(const float* h, const float* g, const float* b, const float* wc,
-                              const float* bc, int M, float* prob, float* logp, cudaStream_t s);
+                              const float* bc, int M, float* prob, float* logp, int tiled, cudaStream_t s);
 
 // window path helpers (k_window.cu)
 cudaError_t launch_boost(const float* prob_nW, int L, int half, int jump, int W,
@@ -155,7 +183,10 @@ cudaError_t launch_boost(const float* prob_nW, int L, int half, int jump, int W,
 // rows of the projected clip gathered into context windows + PE + LayerNorm_1 emit (k_window.cu)
 cudaError_t launch_window_gather_ln(const float* proj, const float* pe, float* out_h, bf16* out_ln,
                                     const float* ln_g, const float* ln_b, long n_rows, int W, int half,
-                                    int jump, cudaStream_t s);
+                                    int jump, int tiled, cudaStream_t s);
+// row-major fp32 residual rows -> tiled layout + LayerNorm(row) in bf16 (fallback front ends, k_window.cu)
+cudaError_t launch_retile_ln(const float* h_rows, float* h_tiled, bf16* out_ln, const float* ln_g,
+                             const float* ln_b, long n_rows, cudaStream_t s);
 
 // log-mel front end (k_logmel.cu): host-built tables and the per-frame FFT + mel + log kernel
 void logmel_tables(int sr, int n_fft, int win, int n_mels, std::vector<float>* fb_dense, std::vector<double>* window);

@@ -47,12 +47,44 @@ def broadcast_weight_blob(blob: Optional[torch.Tensor], numel: int, device: torc
     return buf
 
 
-def load_engine_from_broadcast(engine, state_dict=None, src: int = 0):
-    """Rank ``src`` packs ``state_dict``; all ranks receive the blob and load it."""
+def nccl_comm_ptr(device: torch.device) -> Optional[int]:
+    """The raw ``ncclComm_t`` of the default process group for ``device`` (None when the backend is
+    not NCCL or this torch build does not expose it)."""
+    try:
+        pg = dist.distributed_c10d._get_default_group()
+        backend = pg._get_backend(device)
+        ptr = backend._comm_ptr()
+        return int(ptr) if ptr else None
+    except Exception:
+        return None
+
+
+def load_engine_from_broadcast(engine, state_dict=None, src: int = 0, via: str = "auto"):
+    """Rank ``src`` packs ``state_dict``; all ranks end up with the weights loaded -- ONE collective.
+
+    ``via="c"``: rank ``src`` loads its blob and the library itself broadcasts it from handle to handle
+    (``vadb_broadcast_weights`` on the process group's own ncclComm_t -- the path a maintainer binding only
+    the C ABI would use); ``via="torch"``: ``dist.broadcast`` of the blob, then ``vadb_load_weights``
+    (on_device=1) on every rank; ``"auto"``: the C entry when the NCCL communicator is reachable."""
     from .engine import pack_state
-    blob = None
-    if not dist.is_initialized() or dist.get_rank() == src:
-        blob = pack_state(state_dict, engine.num_layers)
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    is_src = (not multi) or dist.get_rank() == src
+    blob = pack_state(state_dict, engine.num_layers) if is_src else None
+    if multi and via in ("auto", "c") and dist.get_backend() == "nccl":
+        # the communicator is created lazily by the first collective on this device
+        dist.barrier(device_ids=[engine.device.index])
+        comm = nccl_comm_ptr(engine.device)
+        ok = torch.tensor([1 if comm else 0], device=engine.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)            # every rank must take the same path
+        if int(ok.item()) == 1:
+            if is_src:
+                engine.load_blob(blob)
+            engine.broadcast_weights(comm, src)
+            engine.load_path = "vadb_broadcast_weights"
+            return engine
+        if via == "c":
+            raise RuntimeError("the NCCL communicator of the default process group is not reachable")
     buf = broadcast_weight_blob(blob, engine.weight_count, engine.device, src)
     engine.load_blob(buf)
+    engine.load_path = "dist.broadcast + vadb_load_weights"
     return engine

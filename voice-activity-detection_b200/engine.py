@@ -120,6 +120,13 @@ class VadEngine:
                                          1 if on_dev else 0, self._stream_ptr())
         _cabi.check(self._lib, self._h, rc, "vadb_load_weights")
 
+    def broadcast_weights(self, nccl_comm_ptr: int, root: int = 0):
+        """C-level multi-GPU load: one ncclBroadcast of the packed blob from ``root``'s handle into this
+        one (vadb_broadcast_weights).  ``nccl_comm_ptr`` is a raw ``ncclComm_t``.  Collective."""
+        with torch.cuda.device(self.device):
+            rc = self._lib.vadb_broadcast_weights(self._h, C.c_void_p(nccl_comm_ptr), root, self._stream_ptr())
+        _cabi.check(self._lib, self._h, rc, "vadb_broadcast_weights")
+
     def _stream_ptr(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -167,7 +174,9 @@ class VadEngine:
 
     def _forward_host(self, x, lengths, want_logp, want_prob):
         B, T, _ = x.shape
-        x = x.to(torch.float32).contiguous()
+        if x.dtype != torch.bfloat16:       # bf16 host features are uploaded as they are (half the bytes)
+            x = x.to(torch.float32)
+        x = x.contiguous()
         prob = torch.empty((B, T), dtype=torch.float32) if want_prob else None
         logp = torch.empty((B, T, 2), dtype=torch.float32) if want_logp else None
         ln_ptr = None
@@ -175,7 +184,8 @@ class VadEngine:
             lengths = lengths.to(device="cpu", dtype=torch.int32).contiguous()
             ln_ptr = C.c_void_p(lengths.data_ptr())
         rc = self._lib.vadb_forward_host(
-            self._h, C.c_void_p(x.data_ptr()), ln_ptr, B, T,
+            self._h, C.c_void_p(x.data_ptr()),
+            _cabi.VADB_BF16 if x.dtype == torch.bfloat16 else _cabi.VADB_F32, ln_ptr, B, T,
             C.c_void_p(prob.data_ptr()) if want_prob and prob.numel() else None,
             C.c_void_p(logp.data_ptr()) if want_logp and logp.numel() else None)
         _cabi.check(self._lib, self._h, rc, "vadb_forward_host")
@@ -183,19 +193,19 @@ class VadEngine:
 
     def forward_async(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None,
                       want_logp: bool = False, want_prob: bool = True) -> "HostTicket":
-        """Streaming form of the host call: x [B,T,F] fp32 in PINNED host memory; H2D, forward and D2H are
-        only enqueued, so the upload of the next batch overlaps the compute of this one.  Returns a
+        """Streaming form of the host call: x [B,T,F] fp32 or bf16 in PINNED host memory; H2D, forward and
+        D2H are only enqueued, so the upload of the next batch overlaps the compute of this one.  Returns a
         ticket whose ``wait()`` yields (prob, logp) pinned CPU tensors; the output buffers are a ring of
-        four per shape: a result is valid until four further calls."""
-        if x.is_cuda or not x.is_pinned() or x.dtype != torch.float32 or not x.is_contiguous():
-            raise ValueError("forward_async needs a contiguous fp32 tensor in pinned host memory")
+        four per shape: a result is valid until four further calls.  At most four calls may be
+        outstanding (un-waited): a fifth raises RuntimeError without enqueueing anything."""
+        if x.is_cuda or not x.is_pinned() or x.dtype not in (torch.float32, torch.bfloat16) or not x.is_contiguous():
+            raise ValueError("forward_async needs a contiguous fp32/bf16 tensor in pinned host memory")
         if x.dim() != 3 or x.shape[2] != self.feature_size:
             raise ValueError(f"expected [B,T,{self.feature_size}] features, got {tuple(x.shape)}")
         B, T, _ = x.shape
         key = (B, T, want_logp, want_prob)
         ring = self._async_out.setdefault(key, [])
         slot = self._async_n % 4
-        self._async_n += 1
         while len(ring) <= slot:
             ring.append((torch.empty((B, T), dtype=torch.float32).pin_memory() if want_prob else None,
                          torch.empty((B, T, 2), dtype=torch.float32).pin_memory() if want_logp else None))
@@ -206,10 +216,12 @@ class VadEngine:
             ln_ptr = C.c_void_p(keep.data_ptr())
         ticket = C.c_long(-1)
         rc = self._lib.vadb_forward_host_async(
-            self._h, C.c_void_p(x.data_ptr()), ln_ptr, B, T,
+            self._h, C.c_void_p(x.data_ptr()),
+            _cabi.VADB_BF16 if x.dtype == torch.bfloat16 else _cabi.VADB_F32, ln_ptr, B, T,
             C.c_void_p(prob.data_ptr()) if want_prob and prob.numel() else None,
             C.c_void_p(logp.data_ptr()) if want_logp and logp.numel() else None, C.byref(ticket))
         _cabi.check(self._lib, self._h, rc, "vadb_forward_host_async")
+        self._async_n += 1
         return HostTicket(self, ticket.value, prob, logp, (x, keep))
 
     def predict_probabilities(self, feature, half: int, jump: int):
@@ -217,6 +229,10 @@ class VadEngine:
         Returns (probs [L,W], mean [L]) as numpy arrays (host) or CUDA tensors (device)."""
         W = 2 * (half - 1) // jump + 3
         if isinstance(feature, torch.Tensor) and feature.is_cuda:
+            if feature.dim() != 2 or feature.shape[1] != self.feature_size:
+                raise ValueError(f"expected [L,{self.feature_size}] features, got {tuple(feature.shape)}")
+            if feature.device != self.device:
+                raise ValueError(f"features on {feature.device}, engine on {self.device}")
             feat = feature.to(torch.float32).contiguous()
             L = feat.shape[0]
             probs = torch.empty((L, W), dtype=torch.float32, device=self.device)
@@ -280,6 +296,8 @@ class VadEngine:
         fp32 -> CUDA-core kernel, bf16 -> tcgen05 kernel."""
         assert q.is_cuda and q.shape == k.shape == v.shape and q.shape[-1] == 128
         assert q.dtype == k.dtype == v.dtype and q.dtype in (torch.float32, torch.bfloat16)
+        if not (q.device == k.device == v.device == self.device):
+            raise ValueError(f"q/k/v must be on the engine's device {self.device}")
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         B, T, _ = q.shape
         o = torch.empty_like(q)
