@@ -60,6 +60,7 @@ struct vadb_handle {
   bf16* w2_bf = nullptr;     // [L][128*512]
   bf16* win_bf = nullptr;    // [128, 128] front-end weight, columns >= F zero (tensor-core front end)
   unsigned char* wtail = nullptr;   // [L] packed weight blocks of the fused layer-tail kernel (k_tail_tc.cu)
+  float* tail_aux = nullptr;        // [L] folded biases / classifier constants of the same kernel
 
   float* pe = nullptr;       // [pe_T, 128] = PE / sqrt(d)
   int pe_T = 0;
@@ -250,16 +251,10 @@ int run_encoder(vadb_handle* h, const int32_t* lengths, int Bc, int T, float* pr
       const LayerOffsets& lo = h->lay.layers[l];
       if ((rc = attention(h, h->ws_q, h->ws_k, h->ws_v, h->ws_o, VADB_BF16, lengths, Bc, T, s))) return rc;
       TailTcArgs t = {};
-      t.M = M; t.wpack = h->wtail + (size_t)l * tail_pack_bytes(); t.o = (const bf16*)h->ws_o; t.h = h->ws_h;
-      t.bo = w + lo.bo; t.b1 = w + lo.b1; t.b2 = w + lo.b2; t.ln2_g = w + lo.ln2_g; t.ln2_b = w + lo.ln2_b;
-      if (l + 1 < L) {
-        const LayerOffsets& ln = h->lay.layers[l + 1];
-        t.ln1n_g = w + ln.ln1_g; t.ln1n_b = w + ln.ln1_b; t.bqkv = h->bqkv + (size_t)(l + 1) * 3 * D;
-        t.q = (bf16*)h->ws_q; t.k = (bf16*)h->ws_k; t.v = (bf16*)h->ws_v;
-      } else {
-        t.cls_ln_g = w + h->lay.lnf_g; t.cls_ln_b = w + h->lay.lnf_b; t.cls_w = w + h->lay.wc; t.cls_bias = w + h->lay.bc;
-        t.prob = prob; t.logp = logp;
-      }
+      t.M = M; t.wpack = h->wtail + (size_t)l * tail_pack_bytes(); t.aux = h->tail_aux + (size_t)l * tail_aux_floats();
+      t.o = (const bf16*)h->ws_o; t.h = h->ws_h; t.bo = w + lo.bo; t.b2 = w + lo.b2;
+      if (l + 1 < L) { t.q = (bf16*)h->ws_q; t.k = (bf16*)h->ws_k; t.v = (bf16*)h->ws_v; }
+      else { t.prob = prob; t.logp = logp; }
       std::string err;
       cudaError_t e = launch_tail_tc(t, h->num_sms, s, &err);
       if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("tail_tc: ") + cudaGetErrorString(e) + " " + err);
@@ -500,7 +495,7 @@ void vadb_destroy(vadb_handle* h) {
   DeviceGuard dg(h->device);
   cudaDeviceSynchronize();
   free_dev(h->w32); free_dev(h->wqkv); free_dev(h->bqkv);
-  free_dev(h->wqkv_bf); free_dev(h->wo_bf); free_dev(h->w1_bf); free_dev(h->w2_bf); free_dev(h->win_bf); free_dev(h->wtail);
+  free_dev(h->wqkv_bf); free_dev(h->wo_bf); free_dev(h->w1_bf); free_dev(h->w2_bf); free_dev(h->win_bf); free_dev(h->wtail); free_dev(h->tail_aux);
   free_dev(h->pe);
   free_dev(h->ws_h); free_dev(h->ws_q); free_dev(h->ws_k); free_dev(h->ws_v); free_dev(h->ws_o);
   free_dev(h->ws_hid); free_dev(h->ws_prob); free_dev(h->ws_aln);
@@ -540,6 +535,7 @@ static int alloc_weights(vadb_handle* h) {
   CU_TRY(h, cudaMalloc(&h->w2_bf, (size_t)L * D * DFF * sizeof(bf16)));
   CU_TRY(h, cudaMalloc(&h->win_bf, (size_t)D * D * sizeof(bf16)));
   CU_TRY(h, cudaMalloc(&h->wtail, (size_t)L * tail_pack_bytes()));
+  CU_TRY(h, cudaMalloc(&h->tail_aux, (size_t)L * tail_aux_floats() * sizeof(float)));
   return VADB_OK;
 }
 
@@ -565,9 +561,17 @@ static int derive_weights(vadb_handle* h, cudaStream_t s) {
   }
   for (int l = 0; l < L; ++l) {      // fused layer tail: Wo, W1, W2 of layer l + the fused Q|K|V weight of layer l+1
     const LayerOffsets& lo = h->lay.layers[l];
-    CU_TRY(h, launch_tail_pack(h->w32 + lo.wo, h->w32 + lo.w1, h->w32 + lo.w2,
-                               l + 1 < L ? h->wqkv + (size_t)(l + 1) * 3 * D * D : nullptr,
-                               h->wtail + (size_t)l * tail_pack_bytes(), s));
+    TailPackArgs t = {};
+    t.wo = h->w32 + lo.wo; t.w1 = h->w32 + lo.w1; t.b1 = h->w32 + lo.b1; t.w2 = h->w32 + lo.w2;
+    t.ln2_g = h->w32 + lo.ln2_g; t.ln2_b = h->w32 + lo.ln2_b;
+    if (l + 1 < L) {
+      const LayerOffsets& ln = h->lay.layers[l + 1];
+      t.wqkv_next = h->wqkv + (size_t)(l + 1) * 3 * D * D; t.bqkv_next = h->bqkv + (size_t)(l + 1) * 3 * D;
+      t.ln1n_g = h->w32 + ln.ln1_g; t.ln1n_b = h->w32 + ln.ln1_b;
+    } else {
+      t.lnf_g = h->w32 + h->lay.lnf_g; t.lnf_b = h->w32 + h->lay.lnf_b; t.wc = h->w32 + h->lay.wc; t.bc = h->w32 + h->lay.bc;
+    }
+    CU_TRY(h, launch_tail_pack(t, h->wtail + (size_t)l * tail_pack_bytes(), h->tail_aux + (size_t)l * tail_aux_floats(), s));
   }
   CU_TRY(h, cudaStreamSynchronize(s));
   h->loaded = true;

@@ -156,20 +156,26 @@ cudaError_t launch_ffn_tc(const FfnTcArgs& a, int num_sms, cudaStream_t s, std::
 struct TailTcArgs {
   int M;
   const unsigned char* wpack;   // packed weight blocks of this layer (launch_tail_pack)
+  const float* aux;             // folded biases / classifier constants of this layer (launch_tail_pack)
   const bf16* o;                // [M,128] attention output
   float* h;                     // tiled residual stream
-  const float* bo; const float* b1; const float* b2;
-  const float* ln2_g; const float* ln2_b;
-  // not the last layer: next layer's pre-LN, q|k|v biases [384] and the three outputs
-  const float* ln1n_g; const float* ln1n_b; const float* bqkv;
-  bf16* q; bf16* k; bf16* v;    // q == nullptr -> last layer: classifier epilogue
-  const float* cls_ln_g; const float* cls_ln_b; const float* cls_w; const float* cls_bias;
+  const float* bo; const float* b2;
+  bf16* q; bf16* k; bf16* v;    // next layer's attention inputs; q == nullptr -> last layer: classifier epilogue
   float* prob; float* logp;
 };
+// Load-time preparation of one layer: weight blocks in consumption order as the swizzled shared-memory image,
+// LayerNorm gammas folded into the following weights (W diag(gamma)), betas into the following biases
+// (b + W beta), W2 scaled by 1/2 (the kernel computes 2 ReLU), classifier folded with the final LayerNorm.
+struct TailPackArgs {
+  const float* wo; const float* w1; const float* b1; const float* w2;
+  const float* ln2_g; const float* ln2_b;                       // this layer's feed-forward pre-LN
+  const float* wqkv_next; const float* bqkv_next;               // fused [384,128] / [384] of layer l+1, nullptr: last layer
+  const float* ln1n_g; const float* ln1n_b;                     // layer l+1's attention pre-LN
+  const float* lnf_g; const float* lnf_b; const float* wc; const float* bc;   // last layer: final LN + classifier
+};
 size_t tail_pack_bytes();       // bytes of one layer's packed blocks
-// wqkv_next: fused [384,128] q|k|v weight of the next layer, nullptr for the last layer
-cudaError_t launch_tail_pack(const float* wo, const float* w1, const float* w2, const float* wqkv_next,
-                             unsigned char* dst, cudaStream_t s);
+size_t tail_aux_floats();       // floats of one layer's folded biases / constants
+cudaError_t launch_tail_pack(const TailPackArgs& a, unsigned char* dst, float* aux, cudaStream_t s);
 cudaError_t launch_tail_tc(const TailTcArgs& a, int num_sms, cudaStream_t s, std::string* err);
 
 // final LayerNorm + classifier + sigmoid/log-softmax (k_classifier.cu); tiled: h in the tiled residual layout
