@@ -466,3 +466,28 @@ def test_engine_rejects_bad_device_inputs():
         eng.predict_probabilities(torch.zeros(100, 63, device="cuda"), 19, 9)     # wrong feature width
     with pytest.raises(ValueError):
         eng.predict_probabilities(torch.zeros(100, device="cuda"), 19, 9)         # wrong rank
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_attention_kernel_single_tile_tail_items(masked):
+    """B=160, T=512 -> 320 query-tile pairs on 148 SMs: the last 24 pairs become single-tile work items (one
+    warpgroup of the CTA idle, the other MMA warp only keeping the ring protocol).  With masks: even and odd numbers
+    of K/V tiles, a partial last tile, one-tile clips, one key."""
+    eng = engine_for(SYN, "bf16")
+    B, T = 160, 512
+    g = torch.Generator().manual_seed(160)
+    q = (torch.randn(B, T, 128, generator=g) * 1.5).to(torch.bfloat16).cuda()
+    k = (torch.randn(B, T, 128, generator=g) * 1.5).to(torch.bfloat16).cuda()
+    v = torch.randn(B, T, 128, generator=g).to(torch.bfloat16).cuda()
+    lengths = None
+    if masked:
+        lengths = torch.randint(1, T + 1, (B,), generator=g).to(torch.int32)
+        lengths[-12:] = torch.tensor([512, 400, 65, 64, 1, 130, 449, 448, 129, 128, 127, 511], dtype=torch.int32)
+        lengths = lengths.cuda()
+    o = eng.attention(q, k, v, lengths)
+    idx = list(range(0, 140, 23)) + list(range(140, 160))           # the tail clips are the last 12
+    want = _ref_attention(q[idx], k[idx], v[idx], lengths[idx] if masked else None)
+    err = (o[idx].double() - want).abs().max().item()
+    print(f"single-tile tail items, masked={masked}: {err:.3e}")
+    assert torch.isfinite(o).all()
+    assert err <= 2e-2
