@@ -95,6 +95,16 @@ int vadb_reserve(vadb_handle* h, int B, int T);
 int vadb_forward(vadb_handle* h, const void* x, int x_dtype, const int32_t* lengths,
                  int B, int T, float* prob, float* logp, void* stream);
 
+/* Mixed-length batches (BASELINE configs[4]) without the padding work: the same call with the lengths in HOST
+ * memory.  Clips are grouped by ceil(length / 128) * 128 processed frames; every group runs as its own dense batch
+ * with its own key-padding mask, so per-frame kernels and attention see only the frames each clip needs instead of
+ * the batch maximum T (vad/modeling/transformer.py:432-447 builds one [B, T] mask for the padded batch).  Valid
+ * frames (t < lengths[b]) get exactly the results of vadb_forward; frames past a clip's processed length, which
+ * the reference computes from the padding, are returned as 0.
+ *  x             dev [B,T,F] padded batch        lengths_host  HOST int32 [B]        prob / logp  dev, as above */
+int vadb_forward_ragged(vadb_handle* h, const void* x, int x_dtype, const int32_t* lengths_host,
+                        int B, int T, float* prob, float* logp, void* stream);
+
 /* Same call with HOST buffers (pageable or pinned): the library stages them through its
  * pinned buffers, copies H2D, runs the forward and copies the results D2H, on its own
  * stream, and returns when the outputs are in host memory.  This is the end-to-end

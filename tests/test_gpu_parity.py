@@ -364,16 +364,26 @@ def _config5_batch():
     return x, lengths
 
 
+@pytest.mark.parametrize("where", ["device_lengths_padded", "host_lengths_bucketed"])
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-def test_config5_mixed_lengths_every_clip_vs_unpadded_oracle(dtype):
+def test_config5_mixed_lengths_every_clip_vs_unpadded_oracle(dtype, where):
     """BASELINE config 5 (mixed-length batch with padding mask, fp32 vs bf16 sweep): EVERY clip of the
     padded batch, over its valid frames, against the oracle run on the unpadded clip
     (vad/modeling/transformer.py:432-447 mask_from_lengths, :319-325 mask fill)."""
     st = O.make_state(0, 64, 3, 128)
     eng = engine_for(SYN, dtype)
     x, lengths = _config5_batch()
-    prob, _ = eng.forward(x.cuda(), torch.tensor(lengths, dtype=torch.int32).cuda(), want_logp=False)
+    ln = torch.tensor(lengths, dtype=torch.int32)
+    # lengths on the device: one padded batch, as the reference would run it; on the host: length-bucketed
+    # (vadb_forward_ragged), no work on the padding
+    prob, logp = eng.forward(x.cuda(), ln.cuda() if where.startswith("device") else ln)
     p = prob.cpu().numpy()
+    if where.startswith("host"):
+        m = np.arange(x.shape[1])[None, :] >= np.asarray(lengths)[:, None]
+        assert (p[m] == 0).all() and (logp.cpu().numpy()[m] == 0).all()      # frames past a clip: defined as 0
+        p_pad, lp_pad = eng.forward(x.cuda(), ln.cuda())
+        assert np.abs(p_pad.cpu().numpy() - p)[~m].max() <= 1e-5
+        assert np.abs(lp_pad.cpu().numpy() - logp.cpu().numpy())[~m].max() <= 1e-4
     worst, total = 0.0, 0.0
     for b, n in enumerate(lengths):
         want = O.forward_prob(st, x[b:b + 1, :n]).numpy()[0]
@@ -491,3 +501,23 @@ def test_attention_kernel_single_tile_tail_items(masked):
     print(f"single-tile tail items, masked={masked}: {err:.3e}")
     assert torch.isfinite(o).all()
     assert err <= 2e-2
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_ragged_forward_odd_shapes(dtype):
+    """Length-bucketed forward on shapes that are not tile multiples: T = 300 (buckets 128, 256, 300), a clip of
+    length 0 (all keys masked -> NaN rows, as the reference), F = 80 bf16 features, list / numpy lengths."""
+    st = O.make_state(31, 80, 2, 128)
+    from vad_b200.engine import VadEngine
+    eng = VadEngine.from_state_dict(st, compute_dtype=dtype)
+    lengths = [300, 1, 128, 129, 256, 257, 77, 0, 300]
+    x = O.make_input(33, len(lengths), 300, 80)
+    for xin in (x, x.to(torch.bfloat16)):
+        prob, _ = eng.forward(xin.cuda(), np.asarray(lengths), want_logp=False)
+        p = prob.cpu().numpy()
+        for b, n in enumerate(lengths):
+            if n == 0:
+                continue
+            want = O.forward_prob(st, xin[b:b + 1, :n].float()).numpy()[0]
+            assert np.abs(p[b, :n] - want).max() <= TOL[dtype], (b, n)
+    eng.close()

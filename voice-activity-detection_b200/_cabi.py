@@ -13,7 +13,7 @@ SYMBOLS = (
     "vadb_reserve", "vadb_forward", "vadb_forward_host", "vadb_predict_probabilities",
     "vadb_predict_probabilities_host", "vadb_attention", "vadb_positional_table",
     "vadb_launch_count", "vadb_version", "vadb_logmel_frames", "vadb_logmel", "vadb_logmel_tables",
-    "vadb_predict_audio_host", "vadb_forward_host_async", "vadb_host_wait", "vadb_broadcast_weights",
+    "vadb_predict_audio_host", "vadb_forward_host_async", "vadb_host_wait", "vadb_broadcast_weights", "vadb_forward_ragged",
 )
 
 
@@ -53,6 +53,8 @@ def load_library():
     lib.vadb_reserve.restype = i32
     lib.vadb_forward.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
     lib.vadb_forward.restype = i32
+    lib.vadb_forward_ragged.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
+    lib.vadb_forward_ragged.restype = i32
     lib.vadb_forward_host.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp]
     lib.vadb_forward_host.restype = i32
     lib.vadb_predict_probabilities.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]

@@ -49,7 +49,8 @@ using namespace tc;
 
 constexpr int N_EPI_WARPS = 16;
 constexpr int NTHREADS = 32 * (3 + N_EPI_WARPS);   // + producer, MMA issuer, residual-tile mover (last warp)
-constexpr int NW = 3;                              // weight ring stages
+constexpr int NW = 3;                              // weight ring stages (2 stages + two staging slabs per warp: +4 % per forward)
+constexpr int NSTG = 1;                            // staging slabs per epilogue warp
 constexpr uint32_t BLK_BYTES = 128 * 128 * 2;      // [128 x 128] bf16 block = two SW128 halves of 16 KB
 constexpr uint32_t HALF_BYTES = 128 * 128;
 constexpr uint32_t H_BYTES = 128 * 128 * 4;        // one fp32 residual tile
@@ -60,7 +61,7 @@ constexpr uint32_t OFF_W = 0;
 constexpr uint32_t OFF_O = OFF_W + NW * BLK_BYTES;
 constexpr uint32_t OFF_H = OFF_O + BLK_BYTES;
 constexpr uint32_t OFF_STG = OFF_H + H_BYTES;
-constexpr uint32_t OFF_BAR = OFF_STG + N_EPI_WARPS * STG_BYTES;
+constexpr uint32_t OFF_BAR = OFF_STG + NSTG * N_EPI_WARPS * STG_BYTES;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
@@ -345,7 +346,8 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
     const int csel = (warp - 2) >> 2;              // which 32 of the 128 columns
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const uint32_t stg_off = OFF_STG + (uint32_t)(warp - 2) * STG_BYTES;
+    const uint32_t stg_off0 = OFF_STG + (uint32_t)(warp - 2) * NSTG * STG_BYTES;
+    int unit = 0;
     const uint32_t t_aln = tmem_base + lane_addr + TM_ALN + 16u * csel;
     const uint32_t t_x = tmem_base + lane_addr + TM_X;
     // this thread's 32 columns of row `row` of the fp32 residual tile in shared memory: 8 float4 at stride 2 KB,
@@ -519,9 +521,12 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
+          const uint32_t stg_off = stg_off0 + (uint32_t)(unit % NSTG) * STG_BYTES;
+          ++unit;
           if (lane == 0) {
             mbar_arrive(BAR(B_REGFREE + region));
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // this warp's slab is free again
+            // the slab used NSTG stores ago is free again (the TMA engine also carries the 64 KB residual tile)
+            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NSTG - 1) : "memory");
           }
           __syncwarp();
           const float4* bp = reinterpret_cast<const float4*>(p.bqkvp + j * 128 + csel * 32);

@@ -113,6 +113,31 @@ retile_ln_kernel(const float* __restrict__ h_rows, float* __restrict__ h_tiled, 
   }
 }
 
+// Length-bucketed forward: gather the first Tk frames of the listed clips into a dense batch (16-byte vectors;
+// row_bytes is a multiple of 8 and the buffers are 16-byte aligned, so a clip's Tk * row_bytes is a multiple of 16)
+__global__ void gather_clips_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, const int32_t* __restrict__ ids,
+                                    long clip_vec_in, long clip_vec_out, long total) {
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long c = i / clip_vec_out, r = i - c * clip_vec_out;
+    out[i] = __ldg(x + (long)ids[c] * clip_vec_in + r);
+  }
+}
+
+__global__ void scatter_clips_kernel(const float* __restrict__ prob_k, const float* __restrict__ logp_k,
+                                     float* __restrict__ prob, float* __restrict__ logp, const int32_t* __restrict__ ids,
+                                     int T, int Tk, long total) {
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long c = i / Tk, t = i - c * Tk;
+    const long dst = (long)ids[c] * T + t;
+    if (prob) prob[dst] = prob_k[i];
+    if (logp) { logp[dst * 2] = logp_k[i * 2]; logp[dst * 2 + 1] = logp_k[i * 2 + 1]; }
+  }
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
   size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
@@ -168,6 +193,25 @@ cudaError_t launch_boost(const float* prob_nW, int L, int half, int jump, int W,
   int blocks = (L + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   return launch_k(boost_kernel, blocks, 256, 0, s, prob_nW, L, half, jump, W, probs_LW, mean_L);
+}
+
+cudaError_t launch_gather_clips(const void* x, void* out, const int32_t* ids, int n, int T, int Tk, int row_bytes,
+                                cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  if (((long)Tk * row_bytes) % 16 || ((long)T * row_bytes) % 16) return cudaErrorInvalidValue;
+  const long vin = (long)T * row_bytes / 16, vout = (long)Tk * row_bytes / 16, total = vout * n;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  return launch_k(gather_clips_kernel, (unsigned)blocks, 256, 0, s, (const uint4*)x, (uint4*)out, ids, vin, vout, total);
+}
+
+cudaError_t launch_scatter_clips(const float* prob_k, const float* logp_k, float* prob, float* logp, const int32_t* ids,
+                                 int n, int T, int Tk, cudaStream_t s) {
+  if (n <= 0 || (!prob && !logp)) return cudaSuccess;
+  const long total = (long)n * Tk;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  return launch_k(scatter_clips_kernel, (unsigned)blocks, 256, 0, s, prob_k, logp_k, prob, logp, ids, T, Tk, total);
 }
 
 cudaError_t launch_f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t s) {

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <new>
+#include <vector>
 
 #include "vadb_common.cuh"
 
@@ -89,6 +90,10 @@ struct vadb_handle {
   int32_t* dev_len = nullptr; size_t dev_len_n = 0;
   void* win_prob = nullptr; size_t win_prob_bytes = 0;   // [n, W] per-window probabilities
   void* win_proj = nullptr; size_t win_proj_bytes = 0;   // [L, 128] fp32 input projection of the whole clip
+  // length-bucketed forward (vadb_forward_ragged): gathered inputs / outputs of one bucket, clip index lists
+  void* bk_x = nullptr; size_t bk_x_bytes = 0;
+  void* bk_out = nullptr; size_t bk_out_bytes = 0;
+  void* bk_idx = nullptr; size_t bk_idx_bytes = 0;
 
   // log-mel front end (k_logmel.cu): device tables for one (sr, n_fft, win, n_mels) at a time
   int lm_sr = 0, lm_nfft = 0, lm_win = 0, lm_nmels = 0;
@@ -506,6 +511,9 @@ void vadb_destroy(vadb_handle* h) {
   if (h->dev_len) cudaFree(h->dev_len);
   if (h->win_prob) cudaFree(h->win_prob);
   if (h->win_proj) cudaFree(h->win_proj);
+  if (h->bk_x) cudaFree(h->bk_x);
+  if (h->bk_out) cudaFree(h->bk_out);
+  if (h->bk_idx) cudaFree(h->bk_idx);
   if (h->lm_window) cudaFree(h->lm_window);
   if (h->lm_twiddle) cudaFree(h->lm_twiddle);
   if (h->lm_meta) cudaFree(h->lm_meta);
@@ -666,6 +674,81 @@ int vadb_forward(vadb_handle* h, const void* x, int x_dtype, const int32_t* leng
                           prob ? prob + (size_t)b0 * T : nullptr,
                           logp ? logp + (size_t)b0 * T * 2 : nullptr, s)))
       return rc;
+  }
+  return VADB_OK;
+}
+
+// Mixed-length batches without the padding work.  Clips are grouped by their length rounded up to whole 128-frame
+// tiles; each group is gathered into a dense [n, T', F] batch, run through the ordinary forward with its own
+// key-padding mask (lengths), and its results are scattered back to the caller's [B, T] layout.  Per-frame kernels
+// and the attention kernel then only see ceil(len/128)*128 frames per clip instead of T.
+int vadb_forward_ragged(vadb_handle* h, const void* x, int x_dtype, const int32_t* lengths_host, int B, int T,
+                        float* prob, float* logp, void* stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!x || !lengths_host || B < 0 || T < 0) return fail(h, VADB_E_INVALID, "bad forward arguments");
+  if (x_dtype != VADB_F32 && x_dtype != VADB_BF16) return fail(h, VADB_E_INVALID, "x_dtype must be f32 or bf16");
+  if (B == 0 || T == 0) return VADB_OK;
+  DeviceGuard dg(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int F = h->cfg.feature_size;
+  const size_t xsz = x_dtype == VADB_BF16 ? 2 : 4;
+  // bucket key: frames actually processed for the clip
+  std::vector<int> tq(B);
+  std::vector<int> keys;
+  for (int b = 0; b < B; ++b) {
+    const int len = std::min(std::max(lengths_host[b], 0), T);
+    tq[b] = std::min(T, std::max(1, (len + 127) / 128) * 128);
+    keys.push_back(tq[b]);
+  }
+  std::sort(keys.begin(), keys.end());
+  keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+  // device copies of the lengths and of the per-bucket clip lists: [lengths (B) | bucket-ordered clip ids (B) |
+  // bucket-ordered lengths (B)]; the source is pageable memory, so the asynchronous copy stages it before returning
+  std::vector<int32_t> meta(3 * (size_t)B);
+  size_t pos = 0;
+  std::vector<size_t> start(keys.size() + 1, 0);
+  size_t max_in = 0, max_out = 0;
+  for (size_t k = 0; k < keys.size(); ++k) {
+    start[k] = pos;
+    for (int b = 0; b < B; ++b)
+      if (tq[b] == keys[k]) {
+        meta[(size_t)B + pos] = b;
+        meta[2 * (size_t)B + pos] = std::min(std::max(lengths_host[b], 0), T);
+        ++pos;
+      }
+    const size_t n = pos - start[k];
+    max_in = std::max(max_in, n * keys[k] * F * xsz);
+    max_out = std::max(max_out, n * keys[k] * 3 * sizeof(float) + 64);
+  }
+  start[keys.size()] = pos;
+  for (int b = 0; b < B; ++b) meta[b] = std::min(std::max(lengths_host[b], 0), T);
+  if ((rc = ensure_bytes(h, &h->bk_idx, &h->bk_idx_bytes, meta.size() * sizeof(int32_t), false))) return rc;
+  CU_TRY(h, cudaMemcpyAsync(h->bk_idx, meta.data(), meta.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  const int32_t* d_len = (const int32_t*)h->bk_idx;
+  const int32_t* d_ids = d_len + B;
+  const int32_t* d_blen = d_len + 2 * (size_t)B;
+  const bool vec_ok = ((size_t)T * F * xsz) % 16 == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0;
+  if ((keys.size() == 1 && keys[0] == T) || !vec_ok)    // nothing to gain (or rows not 16-byte copyable): padded forward
+    return vadb_forward(h, x, x_dtype, d_len, B, T, prob, logp, stream);
+  if ((rc = ensure_bytes(h, &h->bk_x, &h->bk_x_bytes, max_in, false))) return rc;
+  if ((rc = ensure_bytes(h, &h->bk_out, &h->bk_out_bytes, max_out, false))) return rc;
+  // frames past a clip's processed length are not computed: defined as 0
+  if (prob) CU_TRY(h, cudaMemsetAsync(prob, 0, (size_t)B * T * sizeof(float), s));
+  if (logp) CU_TRY(h, cudaMemsetAsync(logp, 0, (size_t)B * T * 2 * sizeof(float), s));
+  for (size_t k = 0; k < keys.size(); ++k) {
+    const int n = (int)(start[k + 1] - start[k]), Tk = keys[k];
+    const int32_t* ids = d_ids + start[k];
+    cudaError_t e = launch_gather_clips(x, h->bk_x, ids, n, T, Tk, (int)(F * xsz), s);
+    if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("gather: ") + cudaGetErrorString(e));
+    h->launches++;
+    float* pk = (float*)h->bk_out;
+    float* lk = pk + (((size_t)n * Tk + 3) & ~(size_t)3);
+    if ((rc = vadb_forward(h, h->bk_x, x_dtype, d_blen + start[k], n, Tk, prob ? pk : nullptr, logp ? lk : nullptr, stream)))
+      return rc;
+    e = launch_scatter_clips(prob ? pk : nullptr, logp ? lk : nullptr, prob, logp, ids, n, T, Tk, s);
+    if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("scatter: ") + cudaGetErrorString(e));
+    h->launches++;
   }
   return VADB_OK;
 }

@@ -200,6 +200,13 @@ cudaError_t launch_logmel(const float* audio, long n_samples, int n_fft, int hop
                           const double* twiddle, const int* fb_start, const int* fb_len, const int* fb_off,
                           const float* fb_w, int n_mels, float* out, cudaStream_t s);
 
+// length-bucketed forward (k_window.cu): clip rows [ids[i], 0:Tk] of a [B, T, row_bytes] batch -> dense [n, Tk, row_bytes],
+// and the bucket's outputs back to the [B, T] / [B, T, 2] layout
+cudaError_t launch_gather_clips(const void* x, void* out, const int32_t* ids, int n, int T, int Tk, int row_bytes,
+                                cudaStream_t s);
+cudaError_t launch_scatter_clips(const float* prob_k, const float* logp_k, float* prob, float* logp, const int32_t* ids,
+                                 int n, int T, int Tk, cudaStream_t s);
+
 // misc element-wise (k_window.cu)
 cudaError_t launch_pad_rows_bf16(const float* in, bf16* out, int rows, int cols, cudaStream_t s);
 cudaError_t launch_f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t s);

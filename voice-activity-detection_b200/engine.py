@@ -142,11 +142,14 @@ class VadEngine:
                 want_logp: bool = True, want_prob: bool = True):
         """x [B,T,F] fp32/bf16.  CUDA tensor -> async on the current stream, returns CUDA
         tensors; CPU tensor -> end-to-end host call (H2D, forward, D2H), returns CPU tensors.
+        ``lengths`` [B]: key-padding mask j >= lengths[b].  Given on the HOST (CPU tensor, list, numpy) with CUDA
+        features, the batch is run length-bucketed (``vadb_forward_ragged``: no work on the padding, outputs past
+        a clip's processed length are 0); given as a CUDA tensor, as one padded batch like the reference.
         Returns (prob [B,T] fp32 or None, logp [B,T,2] fp32 or None)."""
         if x.dim() != 3 or x.shape[2] != self.feature_size:
             raise ValueError(f"expected [B,T,{self.feature_size}] features, got {tuple(x.shape)}")
         B, T, _ = x.shape
-        if lengths is not None:
+        if lengths is not None and isinstance(lengths, torch.Tensor):
             if lengths.numel() != B:
                 raise ValueError("lengths must have one entry per clip")
         if not x.is_cuda:
@@ -157,11 +160,25 @@ class VadEngine:
             x = x.to(torch.float32)
         x = x.contiguous()
         ln_ptr = None
+        prob = torch.empty((B, T), dtype=torch.float32, device=self.device) if want_prob else None
+        logp = torch.empty((B, T, 2), dtype=torch.float32, device=self.device) if want_logp else None
+        if lengths is not None and not (isinstance(lengths, torch.Tensor) and lengths.is_cuda):
+            host_len = torch.as_tensor(lengths).to(device="cpu", dtype=torch.int32).contiguous()
+            if host_len.numel() != B:
+                raise ValueError("lengths must have one entry per clip")
+            with torch.cuda.device(self.device):
+                rc = self._lib.vadb_forward_ragged(
+                    self._h, C.c_void_p(x.data_ptr()),
+                    _cabi.VADB_BF16 if x.dtype == torch.bfloat16 else _cabi.VADB_F32,
+                    C.c_void_p(host_len.data_ptr()), B, T,
+                    C.c_void_p(prob.data_ptr()) if want_prob and prob.numel() else None,
+                    C.c_void_p(logp.data_ptr()) if want_logp and logp.numel() else None,
+                    self._stream_ptr())
+            _cabi.check(self._lib, self._h, rc, "vadb_forward_ragged")
+            return prob, logp
         if lengths is not None:
             lengths = lengths.to(device=self.device, dtype=torch.int32).contiguous()
             ln_ptr = C.c_void_p(lengths.data_ptr())
-        prob = torch.empty((B, T), dtype=torch.float32, device=self.device) if want_prob else None
-        logp = torch.empty((B, T, 2), dtype=torch.float32, device=self.device) if want_logp else None
         with torch.cuda.device(self.device):
             rc = self._lib.vadb_forward(
                 self._h, C.c_void_p(x.data_ptr()),
@@ -181,7 +198,7 @@ class VadEngine:
         logp = torch.empty((B, T, 2), dtype=torch.float32) if want_logp else None
         ln_ptr = None
         if lengths is not None:
-            lengths = lengths.to(device="cpu", dtype=torch.int32).contiguous()
+            lengths = torch.as_tensor(lengths).to(device="cpu", dtype=torch.int32).contiguous()
             ln_ptr = C.c_void_p(lengths.data_ptr())
         rc = self._lib.vadb_forward_host(
             self._h, C.c_void_p(x.data_ptr()),
@@ -212,7 +229,7 @@ class VadEngine:
         prob, logp = ring[slot]
         ln_ptr, keep = None, None
         if lengths is not None:
-            keep = lengths.to(device="cpu", dtype=torch.int32).contiguous()
+            keep = torch.as_tensor(lengths).to(device="cpu", dtype=torch.int32).contiguous()
             ln_ptr = C.c_void_p(keep.data_ptr())
         ticket = C.c_long(-1)
         rc = self._lib.vadb_forward_host_async(
