@@ -87,6 +87,11 @@ struct TailParams {
   float* logp;                 // [M,2] or nullptr
   int logp_vec;
   bf16* q; bf16* k; bf16* v;   // next layer's attention inputs [M,128]
+  // head mode
+  const float* pe_tiled;       // positional-encoding table / sqrt(d) in the tiled layout, pe_tiles tiles of 128 positions
+  int pe_tiles;                // T / 128 (head mode needs T % 128 == 0): tile t of the batch uses PE tile t % pe_tiles
+  int x_col1;                  // column coordinate of the second half of the feature tile (64: bf16, 32: fp32 as tf32)
+  int x_tf32;                  // features and W_in are fp32 in shared memory, multiplied as tf32
   int stagger_cycles;          // odd CTAs start this many cycles late (de-synchronises the per-tile store bursts)
   long long* trace;            // developer instrumentation (VADB_TAIL_TRACE=1): clock64 stamps of CTA 0's third tile
 };
@@ -123,7 +128,11 @@ __device__ __forceinline__ void ffn_seq(int q, int& is_w2, int& nb) {
 
 #define TT(slot) do { if (TRACE && blockIdx.x == 0 && n == 2 && lane == 0 && p.trace) p.trace[(slot)] = clock64(); } while (0)
 
-template <bool HAS_QKV, bool TRACE>
+// MODE 0: last layer (classifier epilogue), 1: layer tail + next layer's q/k/v, 2: HEAD of the model -- the same
+// machinery for  h0 = x W_in^T + b_in + PE/sqrt(d)  (self_attention.py:13-14, transformer.py:401) followed by layer 0's
+// q,k,v = LN1(h0) Wqkv^T + b: the "O tile" is the feature tile, the "residual tile" is the positional-encoding tile (kept
+// in the same tiled layout), there is no feed-forward phase, and h0 is what gets stored.
+template <int MODE, bool TRACE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_q,
                const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const TailParams p) {
@@ -140,7 +149,8 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.M + 127) >> 7;
-  const int n_wblk = HAS_QKV ? 12 : 9;
+  constexpr bool HAS_QKV = MODE >= 1, HEAD = MODE == 2;
+  const int n_wblk = HEAD ? 4 : HAS_QKV ? 12 : 9;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NW; ++s) { mbar_init(BAR(B_WFULL + s), 1); mbar_init(BAR(B_WEMPTY + s), 1); }
@@ -185,13 +195,14 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
       auto load_h = [&](int tile, int nn) {
         if (nn > 0) mbar_wait(BAR(B_HFREE), (nn - 1) & 1, 57);     // epilogue 1 of the previous tile has read the buffer
         mbar_arrive_expect_tx(BAR(B_HFULL), H_BYTES);
-        bulk_load(smem_base + OFF_H, p.h + (size_t)tile * 16384, H_BYTES, BAR(B_HFULL));
+        const float* src = HEAD ? p.pe_tiled + (size_t)(tile % p.pe_tiles) * 16384 : p.h + (size_t)tile * 16384;
+        bulk_load(smem_base + OFF_H, src, H_BYTES, BAR(B_HFULL));
       };
       auto load_o = [&](int tile, int nn) {
         if (nn > 0) mbar_wait(BAR(B_OEMPTY), (nn - 1) & 1, 41);    // out-projection MMAs of the previous tile retired
         mbar_arrive_expect_tx(BAR(B_OFULL), BLK_BYTES);
         tma_load_2d(smem_base + OFF_O, &tm_o, BAR(B_OFULL), 0, tile * 128);
-        tma_load_2d(smem_base + OFF_O + HALF_BYTES, &tm_o, BAR(B_OFULL), 64, tile * 128);
+        tma_load_2d(smem_base + OFF_O + HALF_BYTES, &tm_o, BAR(B_OFULL), HEAD ? p.x_col1 : 64, tile * 128);
       };
       // the weights do not depend on the previous kernel: the first ring fill overlaps its tail (PDL)
       int pre = 0;
@@ -204,12 +215,14 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
           load_h(tile, 0);
         }
         const int next = tile + (int)gridDim.x;
+        bool o_done = next >= n_tiles;
         for (int b = (n == 0 ? pre : 0); b < n_wblk; ++b) {
           load_w(b);
           TT(200 + b);
           // the O buffer and the residual buffer were released early in this tile: next tile's loads
-          if (b == 5 && next < n_tiles) { load_o(next, n + 1); if (!HAS_QKV) load_h(next, n + 1); TT(220); }
+          if (!o_done && b >= (HEAD ? 2 : 5)) { load_o(next, n + 1); if (!HAS_QKV) load_h(next, n + 1); TT(220); o_done = true; }
         }
+        if (!o_done) { load_o(next, n + 1); if (!HAS_QKV) load_h(next, n + 1); }
       }
     }
   } else if (warp == 1) {
@@ -240,10 +253,17 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
         tc_fence_after();
         if (elect_one()) {
           const uint32_t w_lo = w_lo0 + (uint32_t)ws * (BLK_BYTES >> 4);
+          if (HEAD && p.x_tf32) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_ss_lh(r_acc, o_lo + (kk >> 2) * (HALF_BYTES >> 4) + (kk & 3) * 2,
-                       w_lo + (kk >> 2) * (HALF_BYTES >> 4) + (kk & 3) * 2, DESC_HI_SW128, IDESC, kk != 0 ? 1u : 0u);
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ss_lh_tf32(r_acc, o_lo + (kk >> 2) * (HALF_BYTES >> 4) + (kk & 3) * 2,
+                              w_lo + (kk >> 2) * (HALF_BYTES >> 4) + (kk & 3) * 2, DESC_HI_SW128, idesc_tf32(128, 128), kk != 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ss_lh(r_acc, o_lo + (kk >> 2) * (HALF_BYTES >> 4) + (kk & 3) * 2,
+                         w_lo + (kk >> 2) * (HALF_BYTES >> 4) + (kk & 3) * 2, DESC_HI_SW128, IDESC, kk != 0 ? 1u : 0u);
+          }
           umma_commit(BAR(B_OEMPTY));
           umma_commit(BAR(B_WEMPTY + ws));
           umma_commit(BAR(B_ACC1));
@@ -253,10 +273,12 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
         ++wc;
       }
       // ---- feed-forward: LN2 operand in TMEM (written by the epilogue warps), hidden blocks through TMEM
-      mbar_wait(BAR(B_ALN), aln_use & 1, 45);
-      TT(5);
-      ++aln_use;
-      for (int q = 0; q < 8; ++q, ++wc) {
+      if (!HEAD) {
+        mbar_wait(BAR(B_ALN), aln_use & 1, 45);
+        TT(5);
+        ++aln_use;
+      }
+      for (int q = 0; q < (HEAD ? 0 : 8); ++q, ++wc) {
         int is_w2, nb;
         ffn_seq(q, is_w2, nb);
         const int ws = wc % NW, hs = nb & 1;
@@ -302,6 +324,8 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
           const int ws = wc % NW;
           const uint32_t r_out = j == 0 ? r_hid[0] : j == 1 ? r_hid[1] : r_acc;
           mbar_wait(BAR(B_WFULL + ws), (wc / NW) & 1, 51);
+          // head mode has no hidden blocks in between: q / k land on the previous tile's k / v accumulators
+          if (HEAD && n > 0 && j < 2) mbar_wait(BAR(B_REGFREE + (n + 1 + j) % 3), prev_par, 59);
           TT(52 + 2 * j);
           tc_fence_after();
           if (elect_one()) {
@@ -334,7 +358,8 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
         if (next < n_tiles) {
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           mbar_arrive_expect_tx(BAR(B_HFULL), H_BYTES);
-          bulk_load(smem_base + OFF_H, p.h + (size_t)next * 16384, H_BYTES, BAR(B_HFULL));
+          const float* src = HEAD ? p.pe_tiled + (size_t)(next % p.pe_tiles) * 16384 : p.h + (size_t)next * 16384;
+          bulk_load(smem_base + OFF_H, src, H_BYTES, BAR(B_HFULL));
         }
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -429,67 +454,88 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
           u[4 * i + 3] = __float_as_uint(__uint_as_float(u[4 * i + 3]) + h4.w + b4.w);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(B_HFREE));      // this warp's part of the residual tile is in registers
-      {
+      if (HEAD) {
+        // h0 = x W_in^T + b_in + PE/sqrt(d) (bo = b_in, residual tile = positional-encoding tile): staged in place for the
+        // mover, normalised (LN1 of layer 0, affine part folded into Wqkv') for the q/k/v GEMMs
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          hs_ptr[i * 128] = make_float4(__uint_as_float(u[4 * i]), __uint_as_float(u[4 * i + 1]), __uint_as_float(u[4 * i + 2]),
+                                        __uint_as_float(u[4 * i + 3]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_HSTAGED));
         float rstd, nmr;
         row_norm(u, rstd, nmr);
-        TE(103);
         emit_norm(u, rstd, nmr);
-        const float4* bp = reinterpret_cast<const float4*>(p.b2 + csel * 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b4 = __ldg(bp + i);
-          u[4 * i] = __float_as_uint(__uint_as_float(u[4 * i]) + b4.x);
-          u[4 * i + 1] = __float_as_uint(__uint_as_float(u[4 * i + 1]) + b4.y);
-          u[4 * i + 2] = __float_as_uint(__uint_as_float(u[4 * i + 2]) + b4.z);
-          u[4 * i + 3] = __float_as_uint(__uint_as_float(u[4 * i + 3]) + b4.w);
-        }
-        tmem_st32(r_acc, u);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(B_ALN));
-        TE(104);
-      }
-      // ---- hidden blocks: t = acc + b1';  2 ReLU(t) = t + |t|  -> bf16 pairs over the head of this thread's own columns
-      for (int nb = 0; nb < 4; ++nb) {
-        const int hs = nb & 1;
-        TE(110 + 4 * nb);
-        mbar_wait(BAR(B_HIDFULL + hs), hid_uses[hs] & 1, 53);
-        TE(111 + 4 * nb);
-        hid_uses[hs]++;
-        tc_fence_after();
-        tmem_ld32(r_hid[hs], u);
-        tmem_ld_wait();
-        TE(112 + 4 * nb);
-        uint32_t pk[16];
-        const float4* bp = reinterpret_cast<const float4*>(p.b1p + nb * 128 + csel * 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b4 = __ldg(bp + i);
-          const float t0 = __uint_as_float(u[4 * i]) + b4.x, t1 = __uint_as_float(u[4 * i + 1]) + b4.y;
-          const float t2 = __uint_as_float(u[4 * i + 2]) + b4.z, t3 = __uint_as_float(u[4 * i + 3]) + b4.w;
-          pk[2 * i] = pack_bf16_alu(t0 + fabsf(t0), t1 + fabsf(t1));
-          pk[2 * i + 1] = pack_bf16_alu(t2 + fabsf(t2), t3 + fabsf(t3));
-        }
-        tmem_st16(r_hid[hs], pk);
-        tmem_st_wait();
-        tc_fence_before();
+      } else {
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_HIDBF + hs));
-        TE(113 + 4 * nb);
+        if (lane == 0) mbar_arrive(BAR(B_HFREE));      // this warp's part of the residual tile is in registers
+        {
+          float rstd, nmr;
+          row_norm(u, rstd, nmr);
+          TE(103);
+          emit_norm(u, rstd, nmr);
+          const float4* bp = reinterpret_cast<const float4*>(p.b2 + csel * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b4 = __ldg(bp + i);
+            u[4 * i] = __float_as_uint(__uint_as_float(u[4 * i]) + b4.x);
+            u[4 * i + 1] = __float_as_uint(__uint_as_float(u[4 * i + 1]) + b4.y);
+            u[4 * i + 2] = __float_as_uint(__uint_as_float(u[4 * i + 2]) + b4.z);
+            u[4 * i + 3] = __float_as_uint(__uint_as_float(u[4 * i + 3]) + b4.w);
+          }
+          tmem_st32(r_acc, u);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_ALN));
+          TE(104);
+        }
+        // ---- hidden blocks: t = acc + b1';  2 ReLU(t) = t + |t|  -> bf16 pairs over the head of this thread's own columns
+        for (int nb = 0; nb < 4; ++nb) {
+          const int hs = nb & 1;
+          TE(110 + 4 * nb);
+          mbar_wait(BAR(B_HIDFULL + hs), hid_uses[hs] & 1, 53);
+          TE(111 + 4 * nb);
+          hid_uses[hs]++;
+          tc_fence_after();
+          tmem_ld32(r_hid[hs], u);
+          tmem_ld_wait();
+          TE(112 + 4 * nb);
+          uint32_t pk[16];
+          const float4* bp = reinterpret_cast<const float4*>(p.b1p + nb * 128 + csel * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b4 = __ldg(bp + i);
+            const float t0 = __uint_as_float(u[4 * i]) + b4.x, t1 = __uint_as_float(u[4 * i + 1]) + b4.y;
+            const float t2 = __uint_as_float(u[4 * i + 2]) + b4.z, t3 = __uint_as_float(u[4 * i + 3]) + b4.w;
+            pk[2 * i] = pack_bf16_alu(t0 + fabsf(t0), t1 + fabsf(t1));
+            pk[2 * i + 1] = pack_bf16_alu(t2 + fabsf(t2), t3 + fabsf(t3));
+          }
+          tmem_st16(r_hid[hs], pk);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_HIDBF + hs));
+          TE(113 + 4 * nb);
+        }
       }
       // ---- final epilogue: acc = h'' (residual and b2 were in the accumulator from the start)
-      TE(130);
-      mbar_wait(BAR(B_OUTFULL), n & 1, 54);
-      TE(131);
-      tc_fence_after();
-      tmem_ld32(r_acc, u);
-      tmem_ld_wait();
-      TE(132);
-      const int next = tile + (int)gridDim.x;
+      if (!HEAD) {
+        TE(130);
+        mbar_wait(BAR(B_OUTFULL), n & 1, 54);
+        TE(131);
+        tc_fence_after();
+        tmem_ld32(r_acc, u);
+        tmem_ld_wait();
+        TE(132);
+      }
       if (HAS_QKV) {
+        if (!HEAD) {
         // h'' -> the shared-memory residual tile (its old contents were consumed by epilogue 1 of every warp: all of
         // them have arrived on B_ALN since, which the MMAs behind B_OUTFULL waited for); the mover warp stores it
 #pragma unroll
@@ -509,6 +555,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
         if (lane == 0) mbar_arrive(BAR(B_ALN));
         TE(134);
         TE(135);
+        }
         // ---- q, k, v: + bias' -> bf16 -> 64B-swizzled slab -> TMA store (rows past M clipped by the tensor map)
         for (int j = 0; j < 3; ++j) {
           const uint32_t r_out = j == 0 ? r_hid[0] : j == 1 ? r_hid[1] : r_acc;
@@ -606,19 +653,32 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
 // `scale` and (optionally) per column by col_scale[k] (a folded LayerNorm gamma), as bf16 in the UMMA K-major
 // 128B-swizzled shared-memory image (two 16 KB halves of 64 k each)
 __global__ void pack_block_kernel(const float* __restrict__ w, int ld, int n0, int k0, const float* __restrict__ col_scale,
-                                  float scale, unsigned char* __restrict__ dst) {
+                                  float scale, int k_valid, unsigned char* __restrict__ dst) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;       // one thread per 8 consecutive k of one row
   if (t >= 128 * 16) return;
   const int row = t >> 4, k8 = t & 15;
   const float* src = w + (size_t)(n0 + row) * ld + k0 + k8 * 8;
   float x[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) x[j] = src[j] * scale * (col_scale ? col_scale[k0 + k8 * 8 + j] : 1.0f);
+  for (int j = 0; j < 8; ++j)      // columns >= k_valid: zero (front-end weight [128, F] padded to K = 128)
+    x[j] = (k0 + k8 * 8 + j < k_valid) ? src[j] * scale * (col_scale ? col_scale[k0 + k8 * 8 + j] : 1.0f) : 0.f;
   uint4 o;
   o.x = pack_bf16(x[0], x[1]); o.y = pack_bf16(x[2], x[3]);
   o.z = pack_bf16(x[4], x[5]); o.w = pack_bf16(x[6], x[7]);
   const int half = k8 >> 3, chunk = k8 & 7;
   *reinterpret_cast<uint4*>(dst + half * HALF_BYTES + sw128_offset(row, chunk)) = o;
+}
+
+// fp32 [128, F <= 64] front-end weight -> one 32 KB block of fp32 words for kind::tf32: two halves of [128 rows x 32 k]
+// (128-byte rows, 128B swizzle), columns >= F zero
+__global__ void pack_tf32_kernel(const float* __restrict__ w, int F, unsigned char* __restrict__ dst) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;       // one thread per 4 consecutive k of one row
+  if (t >= 128 * 16) return;
+  const int row = t >> 4, k4 = t & 15;
+  float4 v;
+  v.x = k4 * 4 + 0 < F ? w[(size_t)row * F + k4 * 4 + 0] : 0.f; v.y = k4 * 4 + 1 < F ? w[(size_t)row * F + k4 * 4 + 1] : 0.f;
+  v.z = k4 * 4 + 2 < F ? w[(size_t)row * F + k4 * 4 + 2] : 0.f; v.w = k4 * 4 + 3 < F ? w[(size_t)row * F + k4 * 4 + 3] : 0.f;
+  *reinterpret_cast<float4*>(dst + (k4 >> 3) * HALF_BYTES + sw128_offset(row, k4 & 7)) = v;
 }
 
 // out[n] = bias[n] + sum_k W[n][k] * beta[k]   (LayerNorm beta folded into the bias of the following Linear)
@@ -665,7 +725,7 @@ size_t tail_aux_floats() { return 512 + 384 + 260; }     // b1' | bqkv' | classi
 cudaError_t launch_tail_pack(const TailPackArgs& a, unsigned char* dst, float* aux, cudaStream_t s) {
   int b = 0;
   auto blk = [&](const float* w, int ld, int n0, int k0, const float* cs, float scale) {
-    pack_block_kernel<<<8, 256, 0, s>>>(w, ld, n0, k0, cs, scale, dst + (size_t)b * BLK_BYTES);
+    pack_block_kernel<<<8, 256, 0, s>>>(w, ld, n0, k0, cs, scale, 1 << 30, dst + (size_t)b * BLK_BYTES);
     ++b;
   };
   blk(a.wo, D, 0, 0, nullptr, 1.0f);
@@ -683,11 +743,31 @@ cudaError_t launch_tail_pack(const TailPackArgs& a, unsigned char* dst, float* a
   return cudaGetLastError();
 }
 
+// head of the model: [W_in | Wq' | Wk' | Wv'] for bf16 features (dst_bf16) and, when F <= 64, for fp32 features
+// multiplied as tf32 (dst_tf32: W_in as fp32 words); aux384 = q|k|v biases of layer 0 + Wqkv beta1
+cudaError_t launch_head_pack(const float* w_in, int F, const float* wqkv0, const float* bqkv0, const float* ln1_g,
+                             const float* ln1_b, unsigned char* dst_bf16, unsigned char* dst_tf32, float* aux384,
+                             cudaStream_t s) {
+  if (F <= 128) pack_block_kernel<<<8, 256, 0, s>>>(w_in, F, 0, 0, nullptr, 1.0f, F, dst_bf16);
+  if (F <= 64) pack_tf32_kernel<<<8, 256, 0, s>>>(w_in, F, dst_tf32);
+  for (int j = 0; j < 3; ++j) {
+    pack_block_kernel<<<8, 256, 0, s>>>(wqkv0, D, j * 128, 0, ln1_g, 1.0f, 1 << 30, dst_bf16 + (size_t)(1 + j) * BLK_BYTES);
+    pack_block_kernel<<<8, 256, 0, s>>>(wqkv0, D, j * 128, 0, ln1_g, 1.0f, 1 << 30, dst_tf32 + (size_t)(1 + j) * BLK_BYTES);
+  }
+  fold_bias_kernel<<<2, 256, 0, s>>>(wqkv0, bqkv0, ln1_b, 3 * D, aux384);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_tail_tc(const TailTcArgs& a, int num_sms, cudaStream_t s, std::string* err) {
   if (a.M <= 0) return cudaSuccess;
   const bool has_qkv = a.q != nullptr;
+  const bool head = a.x != nullptr;
+  if (head && (!has_qkv || !a.pe_tiled || a.pe_tiles <= 0)) return cudaErrorInvalidValue;
   CUtensorMap to, tq, tk, tv;
-  CUresult r = tmap2d(&to, a.o, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, 128, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUresult r;
+  if (!head) r = tmap2d(&to, a.o, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, 128, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+  else if (a.x_is_bf16) r = tmap2d(&to, a.x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, a.F, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+  else r = tmap2d(&to, a.x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, a.F, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B);
   if (has_qkv) {
     if (r == CUDA_SUCCESS) r = tmap2d(&tq, a.q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, 128, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     if (r == CUDA_SUCCESS) r = tmap2d(&tk, a.k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.M, 128, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
@@ -703,29 +783,34 @@ cudaError_t launch_tail_tc(const TailTcArgs& a, int num_sms, cudaStream_t s, std
   p.M = a.M; p.wpack = a.wpack; p.h = a.h;
   p.bo = a.bo; p.b2 = a.b2; p.b1p = a.aux; p.bqkvp = a.aux + 512; p.cls_gw = a.aux + 512 + 384;
   p.prob = a.prob; p.logp = a.logp; p.q = a.q; p.k = a.k; p.v = a.v;
+  if (head) {
+    p.bqkvp = a.aux;                      // head aux: only the folded q|k|v biases
+    p.pe_tiled = a.pe_tiled; p.pe_tiles = a.pe_tiles; p.x_col1 = a.x_is_bf16 ? 64 : 32; p.x_tf32 = a.x_is_bf16 ? 0 : 1;
+  }
   p.logp_vec = (reinterpret_cast<uintptr_t>(a.logp) % 8) == 0;
-  if (!a.aux || !a.bo || !a.b2) return cudaErrorInvalidValue;
+  if (!a.aux || !a.bo || (!head && !a.b2)) return cudaErrorInvalidValue;
   static const int stagger = getenv("VADB_TAIL_STAGGER") ? atoi(getenv("VADB_TAIL_STAGGER")) : 0;
   p.stagger_cycles = stagger;
   static thread_local int attr_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (attr_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(tail_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tail_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_dev = dev;
   }
   const int n_tiles = (a.M + 127) / 128;
   const int grid = n_tiles < num_sms ? n_tiles : num_sms;
   static const bool want_trace = getenv("VADB_TAIL_TRACE") != nullptr;
-  if (want_trace && has_qkv) {
+  if (want_trace && has_qkv && !head) {
     long long* dtr = nullptr;
     cudaMalloc(&dtr, 256 * sizeof(long long));
     cudaMemsetAsync(dtr, 0, 256 * sizeof(long long), s);
     p.trace = dtr;
-    tail_tc_kernel<true, true><<<grid, NTHREADS, SMEM_BYTES, s>>>(to, tq, tk, tv, p);
+    tail_tc_kernel<1, true><<<grid, NTHREADS, SMEM_BYTES, s>>>(to, tq, tk, tv, p);
     long long ht[256];
     cudaMemcpyAsync(ht, dtr, sizeof ht, cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
@@ -737,8 +822,9 @@ cudaError_t launch_tail_tc(const TailTcArgs& a, int num_sms, cudaStream_t s, std
     return cudaGetLastError();
   }
   {
-    cudaError_t e = has_qkv ? launch_k(tail_tc_kernel<true, false>, grid, NTHREADS, SMEM_BYTES, s, to, tq, tk, tv, p)
-                            : launch_k(tail_tc_kernel<false, false>, grid, NTHREADS, SMEM_BYTES, s, to, tq, tk, tv, p);
+    cudaError_t e = head ? launch_k(tail_tc_kernel<2, false>, grid, NTHREADS, SMEM_BYTES, s, to, tq, tk, tv, p)
+                  : has_qkv ? launch_k(tail_tc_kernel<1, false>, grid, NTHREADS, SMEM_BYTES, s, to, tq, tk, tv, p)
+                            : launch_k(tail_tc_kernel<0, false>, grid, NTHREADS, SMEM_BYTES, s, to, tq, tk, tv, p);
     if (e != cudaSuccess) return e;
   }
   return cudaGetLastError();

@@ -62,6 +62,12 @@ struct vadb_handle {
   bf16* win_bf = nullptr;    // [128, 128] front-end weight, columns >= F zero (tensor-core front end)
   unsigned char* wtail = nullptr;   // [L] packed weight blocks of the fused layer-tail kernel (k_tail_tc.cu)
   float* tail_aux = nullptr;        // [L] folded biases / classifier constants of the same kernel
+  unsigned char* head_bf16 = nullptr;   // head of the model (front end + layer 0's q/k/v in the tail kernel's head mode):
+  unsigned char* head_tf32 = nullptr;   //   4 weight blocks for bf16 features / for fp32 features as tf32 (F <= 64)
+  float* head_aux = nullptr;            //   folded q|k|v biases of layer 0
+  float* pe_tiled = nullptr;            // PE / sqrt(d) of pe_tiled_T positions in the tiled layout (head mode)
+  int pe_tiled_T = 0;
+  bool qkv_ready = false;               // ws_q/k/v already hold layer 0's attention inputs (written by the head kernel)
 
   float* pe = nullptr;       // [pe_T, 128] = PE / sqrt(d)
   int pe_T = 0;
@@ -165,6 +171,25 @@ int ensure_pe(vadb_handle* h, int T) {
   return VADB_OK;
 }
 
+// PE / sqrt(d) for positions [0, T) in the tiled layout of the residual stream ([T/128 tiles][32 column quads][128 rows]
+// [4 floats]): the head kernel bulk-loads one 64 KB tile of it per 128 frames
+int ensure_pe_tiled(vadb_handle* h, int T) {
+  if (T == h->pe_tiled_T) return VADB_OK;
+  if (T % 128 || T > h->pe_T) return fail(h, VADB_E_INVALID, "internal: tiled positional table needs T % 128 == 0");
+  std::vector<float> rows((size_t)T * D), tiled((size_t)T * D);
+  CU_TRY(h, cudaDeviceSynchronize());
+  CU_TRY(h, cudaMemcpy(rows.data(), h->pe, rows.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  for (int t = 0; t < T; ++t)
+    for (int c = 0; c < D; ++c)
+      tiled[(size_t)(t >> 7) * 16384 + (size_t)(c >> 2) * 512 + (size_t)(t & 127) * 4 + (c & 3)] = rows[(size_t)t * D + c];
+  free_dev(h->pe_tiled);
+  h->pe_tiled_T = 0;
+  CU_TRY(h, cudaMalloc(&h->pe_tiled, tiled.size() * sizeof(float)));
+  CU_TRY(h, cudaMemcpy(h->pe_tiled, tiled.data(), tiled.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->pe_tiled_T = T;
+  return VADB_OK;
+}
+
 int ensure_workspace(vadb_handle* h, size_t frames) {
   if (frames <= h->cap_frames) return VADB_OK;
   size_t cap = std::max(frames, h->cap_frames + h->cap_frames / 2);
@@ -241,7 +266,7 @@ int run_encoder(vadb_handle* h, const int32_t* lengths, int Bc, int T, float* pr
     // also produces q,k,v of layer l+1, the last one the probabilities (2 + 2L launches per forward)
     const int L = h->cfg.num_layers;
     int rc;
-    {
+    if (!h->qkv_ready) {
       const LayerOffsets& lo = h->lay.layers[0];
       GemmTcArgs g = {};
       g.M = M; g.N = 3 * D; g.K = D; g.w_bf16 = h->wqkv_bf;
@@ -266,6 +291,7 @@ int run_encoder(vadb_handle* h, const int32_t* lengths, int Bc, int T, float* pr
       h->launches++;
     }
     h->aln_valid = false;
+    h->qkv_ready = false;
     return VADB_OK;
   }
   for (int l = 0; l < h->cfg.num_layers; ++l) {
@@ -500,7 +526,8 @@ void vadb_destroy(vadb_handle* h) {
   DeviceGuard dg(h->device);
   cudaDeviceSynchronize();
   free_dev(h->w32); free_dev(h->wqkv); free_dev(h->bqkv);
-  free_dev(h->wqkv_bf); free_dev(h->wo_bf); free_dev(h->w1_bf); free_dev(h->w2_bf); free_dev(h->win_bf); free_dev(h->wtail); free_dev(h->tail_aux);
+  free_dev(h->wqkv_bf); free_dev(h->wo_bf); free_dev(h->w1_bf); free_dev(h->w2_bf); free_dev(h->win_bf); free_dev(h->wtail); free_dev(h->tail_aux); free_dev(h->head_bf16); free_dev(h->head_tf32); free_dev(h->head_aux);
+  free_dev(h->pe_tiled);
   free_dev(h->pe);
   free_dev(h->ws_h); free_dev(h->ws_q); free_dev(h->ws_k); free_dev(h->ws_v); free_dev(h->ws_o);
   free_dev(h->ws_hid); free_dev(h->ws_prob); free_dev(h->ws_aln);
@@ -544,6 +571,9 @@ static int alloc_weights(vadb_handle* h) {
   CU_TRY(h, cudaMalloc(&h->win_bf, (size_t)D * D * sizeof(bf16)));
   CU_TRY(h, cudaMalloc(&h->wtail, (size_t)L * tail_pack_bytes()));
   CU_TRY(h, cudaMalloc(&h->tail_aux, (size_t)L * tail_aux_floats() * sizeof(float)));
+  CU_TRY(h, cudaMalloc(&h->head_bf16, 4 * (size_t)32768));
+  CU_TRY(h, cudaMalloc(&h->head_tf32, 4 * (size_t)32768));
+  CU_TRY(h, cudaMalloc(&h->head_aux, 3 * D * sizeof(float)));
   return VADB_OK;
 }
 
@@ -581,6 +611,8 @@ static int derive_weights(vadb_handle* h, cudaStream_t s) {
     }
     CU_TRY(h, launch_tail_pack(t, h->wtail + (size_t)l * tail_pack_bytes(), h->tail_aux + (size_t)l * tail_aux_floats(), s));
   }
+  CU_TRY(h, launch_head_pack(h->w32 + h->lay.w_in, h->cfg.feature_size, h->wqkv, h->bqkv, h->w32 + h->lay.layers[0].ln1_g,
+                             h->w32 + h->lay.layers[0].ln1_b, h->head_bf16, h->head_tf32, h->head_aux, s));
   CU_TRY(h, cudaStreamSynchronize(s));
   h->loaded = true;
   return VADB_OK;
@@ -666,9 +698,26 @@ int vadb_forward(vadb_handle* h, const void* x, int x_dtype, const int32_t* leng
   if ((rc = ensure_workspace(h, (size_t)cpp * T))) return rc;
   const int F = h->cfg.feature_size;
   const size_t xsz = x_dtype == VADB_BF16 ? 2 : 4;
+  // Head of the model in ONE kernel (front end + layer 0's q/k/v: the tail kernel's head mode) when a 128-frame tile
+  // never wraps around the positional table and the features fit its operand tile; VADB_FUSE_HEAD=0: two kernels
+  static const bool head_ok = !(getenv("VADB_FUSE_HEAD") && atoi(getenv("VADB_FUSE_HEAD")) == 0);
+  const bool use_head = head_ok && fuse_tail(h) && T % 128 == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0 &&
+                        (x_dtype == VADB_BF16 ? (F % 8 == 0 && F <= 128) : (F % 4 == 0 && F <= 64));
+  if (use_head && (rc = ensure_pe_tiled(h, T))) return rc;
   for (int b0 = 0; b0 < B; b0 += cpp) {
     const int Bc = std::min(cpp, B - b0);
-    if ((rc = front_end(h, (const char*)x + (size_t)b0 * T * F * xsz, x_dtype == VADB_BF16, Bc * T, T, 0, 0, 0, s)))
+    if (use_head) {
+      TailTcArgs t = {};
+      t.M = Bc * T; t.x = (const char*)x + (size_t)b0 * T * F * xsz; t.x_is_bf16 = x_dtype == VADB_BF16; t.F = F;
+      t.wpack = x_dtype == VADB_BF16 ? h->head_bf16 : h->head_tf32; t.aux = h->head_aux;
+      t.bo = h->w32 + h->lay.b_in; t.h = h->ws_h; t.pe_tiled = h->pe_tiled; t.pe_tiles = T / 128;
+      t.q = (bf16*)h->ws_q; t.k = (bf16*)h->ws_k; t.v = (bf16*)h->ws_v;
+      std::string err;
+      cudaError_t e = launch_tail_tc(t, h->num_sms, s, &err);
+      if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("head_tc: ") + cudaGetErrorString(e) + " " + err);
+      h->launches++;
+      h->qkv_ready = true;
+    } else if ((rc = front_end(h, (const char*)x + (size_t)b0 * T * F * xsz, x_dtype == VADB_BF16, Bc * T, T, 0, 0, 0, s)))
       return rc;
     if ((rc = run_encoder(h, lengths ? lengths + b0 : nullptr, Bc, T,
                           prob ? prob + (size_t)b0 * T : nullptr,

@@ -162,6 +162,10 @@ struct TailTcArgs {
   const float* bo; const float* b2;
   bf16* q; bf16* k; bf16* v;    // next layer's attention inputs; q == nullptr -> last layer: classifier epilogue
   float* prob; float* logp;
+  // head of the model (x != nullptr): h0 = x W_in^T + b_in + PE/sqrt(d) and layer 0's q,k,v in the same kernel;
+  // wpack = launch_head_pack's blocks for the feature dtype, aux = its folded q|k|v biases, bo = b_in, h = output
+  const void* x; int x_is_bf16; int F;
+  const float* pe_tiled; int pe_tiles;     // PE/sqrt(d) in the tiled layout, T / 128 tiles (needs T % 128 == 0)
 };
 // Load-time preparation of one layer: weight blocks in consumption order as the swizzled shared-memory image,
 // LayerNorm gammas folded into the following weights (W diag(gamma)), betas into the following biases
@@ -177,6 +181,9 @@ size_t tail_pack_bytes();       // bytes of one layer's packed blocks
 size_t tail_aux_floats();       // floats of one layer's folded biases / constants
 cudaError_t launch_tail_pack(const TailPackArgs& a, unsigned char* dst, float* aux, cudaStream_t s);
 cudaError_t launch_tail_tc(const TailTcArgs& a, int num_sms, cudaStream_t s, std::string* err);
+cudaError_t launch_head_pack(const float* w_in, int F, const float* wqkv0, const float* bqkv0, const float* ln1_g,
+                             const float* ln1_b, unsigned char* dst_bf16, unsigned char* dst_tf32, float* aux384,
+                             cudaStream_t s);
 
 // final LayerNorm + classifier + sigmoid/log-softmax (k_classifier.cu); tiled: h in the tiled residual layout
 cudaError_t launch_classifier(const float* h, const float* g, const float* b, const float* wc,
