@@ -1121,18 +1121,26 @@ int vadb_predict_audio_host(vadb_handle* h, const float* audio, long n_samples, 
   const size_t a_bytes = (size_t)n_samples * sizeof(float);
   if ((rc = ensure_bytes(h, &h->lm_audio, &h->lm_audio_bytes, a_bytes, false))) return rc;
   if ((rc = ensure_bytes(h, &h->lm_feat, &h->lm_feat_bytes, (size_t)L * F * sizeof(float), false))) return rc;
-  // upload in chunks through the two pinned staging slots: the memcpy of chunk i+1 overlaps the DMA of chunk i
-  const size_t CH = (size_t)4 << 20;
-  if ((rc = ensure_bytes(h, &h->pin_in, &h->pin_in_bytes, 2 * CH, true))) return rc;
-  int n_ch = 0;
-  for (size_t off = 0; off < a_bytes; off += CH, ++n_ch) {
-    const size_t nb = std::min(CH, a_bytes - off);
-    const int slot = n_ch & 1;
-    char* stage = (char*)h->pin_in + (size_t)slot * CH;
-    if (n_ch >= 2) CU_TRY(h, cudaEventSynchronize(h->ev_h2d[slot]));
-    memcpy(stage, (const char*)audio + off, nb);
-    CU_TRY(h, cudaMemcpyAsync((char*)h->lm_audio + off, stage, nb, cudaMemcpyHostToDevice, s));
-    CU_TRY(h, cudaEventRecord(h->ev_h2d[slot], s));
+  cudaPointerAttributes pa;
+  const bool audio_pinned = cudaPointerGetAttributes(&pa, audio) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+  if (!audio_pinned) cudaGetLastError();
+  if (audio_pinned) {
+    // caller's buffer is page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory): one DMA, no staging copy
+    CU_TRY(h, cudaMemcpyAsync(h->lm_audio, audio, a_bytes, cudaMemcpyHostToDevice, s));
+  } else {
+    // upload in chunks through the two pinned staging slots: the memcpy of chunk i+1 overlaps the DMA of chunk i
+    const size_t CH = (size_t)4 << 20;
+    if ((rc = ensure_bytes(h, &h->pin_in, &h->pin_in_bytes, 2 * CH, true))) return rc;
+    int n_ch = 0;
+    for (size_t off = 0; off < a_bytes; off += CH, ++n_ch) {
+      const size_t nb = std::min(CH, a_bytes - off);
+      const int slot = n_ch & 1;
+      char* stage = (char*)h->pin_in + (size_t)slot * CH;
+      if (n_ch >= 2) CU_TRY(h, cudaEventSynchronize(h->ev_h2d[slot]));
+      memcpy(stage, (const char*)audio + off, nb);
+      CU_TRY(h, cudaMemcpyAsync((char*)h->lm_audio + off, stage, nb, cudaMemcpyHostToDevice, s));
+      CU_TRY(h, cudaEventRecord(h->ev_h2d[slot], s));
+    }
   }
   if ((rc = vadb_logmel(h, (const float*)h->lm_audio, n_samples, sample_rate, n_fft, hop, win, F,
                         (float*)h->lm_feat, s)))
