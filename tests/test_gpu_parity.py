@@ -521,3 +521,21 @@ def test_ragged_forward_odd_shapes(dtype):
             want = O.forward_prob(st, xin[b:b + 1, :n].float()).numpy()[0]
             assert np.abs(p[b, :n] - want).max() <= TOL[dtype], (b, n)
     eng.close()
+
+
+def test_ragged_forward_concurrent_buckets_equal_sequential(monkeypatch):
+    """vadb_forward_ragged spreads its length buckets over three streams (separate workspace slices); the result
+    must be bit-identical to running the buckets one after the other (VADB_BUCKET_STREAMS=0), call after call."""
+    eng = engine_for(SYN, "bf16")
+    x, lengths = _config5_batch()
+    ln = torch.tensor(lengths, dtype=torch.int32)
+    xg = x.cuda()
+    outs = []
+    for mode in ("1", "0", "1"):
+        monkeypatch.setenv("VADB_BUCKET_STREAMS", mode)
+        for _ in range(3):
+            prob, logp = eng.forward(xg, ln)
+        torch.cuda.synchronize()
+        outs.append((prob.cpu().numpy().copy(), logp.cpu().numpy().copy()))
+    for p, lp in outs[1:]:
+        assert np.array_equal(p, outs[0][0], equal_nan=True) and np.array_equal(lp, outs[0][1], equal_nan=True)

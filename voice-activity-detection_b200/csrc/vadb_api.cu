@@ -100,6 +100,8 @@ struct vadb_handle {
   void* bk_x = nullptr; size_t bk_x_bytes = 0;
   void* bk_out = nullptr; size_t bk_out_bytes = 0;
   void* bk_idx = nullptr; size_t bk_idx_bytes = 0;
+  cudaStream_t bk_stream[2] = {nullptr, nullptr};      // side streams: length buckets run concurrently
+  cudaEvent_t bk_fork = nullptr, bk_join[2] = {nullptr, nullptr};
 
   // log-mel front end (k_logmel.cu): device tables for one (sr, n_fft, win, n_mels) at a time
   int lm_sr = 0, lm_nfft = 0, lm_win = 0, lm_nmels = 0;
@@ -174,7 +176,7 @@ int ensure_pe(vadb_handle* h, int T) {
 // PE / sqrt(d) for positions [0, T) in the tiled layout of the residual stream ([T/128 tiles][32 column quads][128 rows]
 // [4 floats]): the head kernel bulk-loads one 64 KB tile of it per 128 frames
 int ensure_pe_tiled(vadb_handle* h, int T) {
-  if (T == h->pe_tiled_T) return VADB_OK;
+  if (T <= h->pe_tiled_T) return VADB_OK;     // tile j of the table is positions 128 j ..: a longer table serves every shorter T
   if (T % 128 || T > h->pe_T) return fail(h, VADB_E_INVALID, "internal: tiled positional table needs T % 128 == 0");
   std::vector<float> rows((size_t)T * D), tiled((size_t)T * D);
   CU_TRY(h, cudaDeviceSynchronize());
@@ -547,6 +549,11 @@ void vadb_destroy(vadb_handle* h) {
   if (h->lm_w) cudaFree(h->lm_w);
   if (h->lm_audio) cudaFree(h->lm_audio);
   if (h->lm_feat) cudaFree(h->lm_feat);
+  for (int i = 0; i < 2; ++i) {
+    if (h->bk_stream[i]) cudaStreamDestroy(h->bk_stream[i]);
+    if (h->bk_join[i]) cudaEventDestroy(h->bk_join[i]);
+  }
+  if (h->bk_fork) cudaEventDestroy(h->bk_fork);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->own_stream2) cudaStreamDestroy(h->own_stream2);
   for (int i = 0; i < 2; ++i) {
@@ -780,25 +787,79 @@ int vadb_forward_ragged(vadb_handle* h, const void* x, int x_dtype, const int32_
   const bool vec_ok = ((size_t)T * F * xsz) % 16 == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0;
   if ((keys.size() == 1 && keys[0] == T) || !vec_ok)    // nothing to gain (or rows not 16-byte copyable): padded forward
     return vadb_forward(h, x, x_dtype, d_len, B, T, prob, logp, stream);
-  if ((rc = ensure_bytes(h, &h->bk_x, &h->bk_x_bytes, max_in, false))) return rc;
-  if ((rc = ensure_bytes(h, &h->bk_out, &h->bk_out_bytes, max_out, false))) return rc;
+  // Buckets are independent forwards: each gets its own slice of the gather buffers and of the workspace and they
+  // are spread over the caller's stream and two side streams, so the short buckets' small grids run in the SMs the
+  // long bucket's last wave leaves idle instead of each costing a chain of launch latencies.
+  const size_t K = keys.size();
+  std::vector<size_t> in_off(K + 1, 0), out_off(K + 1, 0), ws_off(K + 1, 0);
+  for (size_t k = 0; k < K; ++k) {
+    const size_t n = start[k + 1] - start[k];
+    in_off[k + 1] = in_off[k] + ((n * keys[k] * F * xsz + 255) & ~(size_t)255);
+    out_off[k + 1] = out_off[k] + ((n * keys[k] * 3 * sizeof(float) + 64 + 255) & ~(size_t)255);
+    ws_off[k + 1] = ws_off[k] + n * keys[k];              // frames; multiples of 128 (whole tiles) unless the key is T itself
+    if (ws_off[k + 1] % 128) ws_off[k + 1] += 128 - ws_off[k + 1] % 128;
+  }
+  const bool concurrent = K > 1 && ws_off[K] <= MAX_FRAMES_PER_PASS &&
+                          !(getenv("VADB_BUCKET_STREAMS") && atoi(getenv("VADB_BUCKET_STREAMS")) == 0);
+  if ((rc = ensure_bytes(h, &h->bk_x, &h->bk_x_bytes, concurrent ? in_off[K] : max_in, false))) return rc;
+  if ((rc = ensure_bytes(h, &h->bk_out, &h->bk_out_bytes, concurrent ? out_off[K] : max_out, false))) return rc;
+  if (concurrent) {
+    // everything that may (re)allocate happens before the fork
+    if ((rc = ensure_pe(h, keys.back()))) return rc;
+    if ((rc = ensure_workspace(h, ws_off[K]))) return rc;
+    if (fuse_tail(h) && keys.back() % 128 == 0 && (rc = ensure_pe_tiled(h, keys.back()))) return rc;
+    for (int i = 0; i < 2; ++i) {
+      if (!h->bk_stream[i]) CU_TRY(h, cudaStreamCreateWithFlags(&h->bk_stream[i], cudaStreamNonBlocking));
+      if (!h->bk_join[i]) CU_TRY(h, cudaEventCreateWithFlags(&h->bk_join[i], cudaEventDisableTiming));
+    }
+    if (!h->bk_fork) CU_TRY(h, cudaEventCreateWithFlags(&h->bk_fork, cudaEventDisableTiming));
+  }
   // frames past a clip's processed length are not computed: defined as 0
   if (prob) CU_TRY(h, cudaMemsetAsync(prob, 0, (size_t)B * T * sizeof(float), s));
   if (logp) CU_TRY(h, cudaMemsetAsync(logp, 0, (size_t)B * T * 2 * sizeof(float), s));
-  for (size_t k = 0; k < keys.size(); ++k) {
+  if (concurrent) {
+    CU_TRY(h, cudaEventRecord(h->bk_fork, s));
+    for (int i = 0; i < 2; ++i) CU_TRY(h, cudaStreamWaitEvent(h->bk_stream[i], h->bk_fork, 0));
+  }
+  // longest bucket first on the caller's stream, the others alternate over the side streams
+  struct WsView {            // the handle's workspace pointers shifted to one bucket's slice while its work is enqueued
+    vadb_handle* h; bool on; size_t cap; float* hh; void *q, *k, *v, *o, *hid; bf16* aln; float* pr;
+    WsView(vadb_handle* hd, bool active, size_t off, size_t frames, size_t act) : h(hd), on(active), cap(hd->cap_frames), hh(hd->ws_h),
+        q(hd->ws_q), k(hd->ws_k), v(hd->ws_v), o(hd->ws_o), hid(hd->ws_hid), aln(hd->ws_aln), pr(hd->ws_prob) {
+      if (!on) return;       // sequential buckets use (and may grow) the whole workspace
+      h->ws_h += off * D; h->ws_q = (char*)q + off * D * act; h->ws_k = (char*)k + off * D * act; h->ws_v = (char*)v + off * D * act;
+      h->ws_o = (char*)o + off * D * act; h->ws_hid = (char*)hid + off * DFF * act; h->ws_aln += off * D; h->ws_prob += off;
+      h->cap_frames = frames;
+    }
+    ~WsView() { if (!on) return; h->cap_frames = cap; h->ws_h = hh; h->ws_q = q; h->ws_k = k; h->ws_v = v; h->ws_o = o; h->ws_hid = hid; h->ws_aln = aln; h->ws_prob = pr; }
+  };
+  const size_t act = is_bf16_mode(h) ? sizeof(bf16) : sizeof(float);
+  int side = 0;
+  for (size_t kk = 0; kk < K; ++kk) {
+    const size_t k = K - 1 - kk;
     const int n = (int)(start[k + 1] - start[k]), Tk = keys[k];
+    cudaStream_t sk = (!concurrent || kk == 0) ? s : h->bk_stream[side++ & 1];
     const int32_t* ids = d_ids + start[k];
-    cudaError_t e = launch_gather_clips(x, h->bk_x, ids, n, T, Tk, (int)(F * xsz), s);
+    char* xin = (char*)h->bk_x + (concurrent ? in_off[k] : 0);
+    cudaError_t e = launch_gather_clips(x, xin, ids, n, T, Tk, (int)(F * xsz), sk);
     if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("gather: ") + cudaGetErrorString(e));
     h->launches++;
-    float* pk = (float*)h->bk_out;
+    float* pk = (float*)((char*)h->bk_out + (concurrent ? out_off[k] : 0));
     float* lk = pk + (((size_t)n * Tk + 3) & ~(size_t)3);
-    if ((rc = vadb_forward(h, h->bk_x, x_dtype, d_blen + start[k], n, Tk, prob ? pk : nullptr, logp ? lk : nullptr, stream)))
-      return rc;
-    e = launch_scatter_clips(prob ? pk : nullptr, logp ? lk : nullptr, prob, logp, ids, n, T, Tk, s);
+    {
+      WsView view(h, concurrent, ws_off[k], ws_off[k + 1] - ws_off[k], act);
+      rc = vadb_forward(h, xin, x_dtype, d_blen + start[k], n, Tk, prob ? pk : nullptr, logp ? lk : nullptr, (void*)sk);
+    }
+    if (rc) return rc;
+    e = launch_scatter_clips(prob ? pk : nullptr, logp ? lk : nullptr, prob, logp, ids, n, T, Tk, sk);
     if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("scatter: ") + cudaGetErrorString(e));
     h->launches++;
   }
+  if (concurrent)
+    for (int i = 0; i < 2; ++i) {
+      CU_TRY(h, cudaEventRecord(h->bk_join[i], h->bk_stream[i]));
+      CU_TRY(h, cudaStreamWaitEvent(s, h->bk_join[i], 0));
+    }
   return VADB_OK;
 }
 
