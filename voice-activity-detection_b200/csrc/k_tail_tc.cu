@@ -150,10 +150,14 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.M + 127) >> 7;
   constexpr bool HAS_QKV = MODE >= 1, HEAD = MODE == 2;
+  // The last-layer variant stages no q|k|v: its 32 KB slab region is a fourth weight-ring stage (the FFN phase of that
+  // variant otherwise stalls ~1.7 k cycles per tile on a block whose stage was released too late for the L2 latency)
+  constexpr int NWK = HAS_QKV ? NW : 4;
+  auto wslot_blk = [](int s) { return s == 3 ? (int)((OFF_STG - OFF_W) / BLK_BYTES) : s; };
   const int n_wblk = HEAD ? 4 : HAS_QKV ? 12 : 9;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NW; ++s) { mbar_init(BAR(B_WFULL + s), 1); mbar_init(BAR(B_WEMPTY + s), 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(BAR(B_WFULL + s), 1); mbar_init(BAR(B_WEMPTY + s), 1); }
     mbar_init(BAR(B_OFULL), 1); mbar_init(BAR(B_OEMPTY), 1);
     mbar_init(BAR(B_ACC1), 1);
     mbar_init(BAR(B_ALN), N_EPI_WARPS);
@@ -185,10 +189,10 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
     if (lane == 0) {
       int wc = 0;                                  // weight blocks issued so far
       auto load_w = [&](int b) {
-        const int s = wc % NW;
-        mbar_wait(BAR(B_WEMPTY + s), ((wc / NW) & 1) ^ 1, 40);
+        const int s = wc % NWK;
+        mbar_wait(BAR(B_WEMPTY + s), ((wc / NWK) & 1) ^ 1, 40);
         mbar_arrive_expect_tx(BAR(B_WFULL + s), BLK_BYTES);
-        bulk_load(smem_base + OFF_W + s * BLK_BYTES, p.wpack + (size_t)b * BLK_BYTES, BLK_BYTES, BAR(B_WFULL + s));
+        bulk_load(smem_base + OFF_W + wslot_blk(s) * BLK_BYTES, p.wpack + (size_t)b * BLK_BYTES, BLK_BYTES, BAR(B_WFULL + s));
         ++wc;
       };
       int n = 0;
@@ -207,7 +211,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
       // the weights do not depend on the previous kernel: the first ring fill overlaps its tail (PDL)
       int pre = 0;
       if ((int)blockIdx.x < n_tiles)
-        for (; pre < NW && pre < n_wblk; ++pre) load_w(pre);
+        for (; pre < NWK && pre < n_wblk; ++pre) load_w(pre);
       pdl_wait();
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
         if (n == 0) {
@@ -246,13 +250,13 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
       TT(1);
       if (n > 0 && HAS_QKV) mbar_wait(BAR(B_REGFREE + n % 3), prev_par, 43);           // q of the previous tile drained
       {
-        const int ws = wc % NW;
+        const int ws = wc % NWK;
         TT(2);
-        mbar_wait(BAR(B_WFULL + ws), (wc / NW) & 1, 44);
+        mbar_wait(BAR(B_WFULL + ws), (wc / NWK) & 1, 44);
         TT(3);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t w_lo = w_lo0 + (uint32_t)ws * (BLK_BYTES >> 4);
+          const uint32_t w_lo = w_lo0 + (uint32_t)wslot_blk(ws) * (BLK_BYTES >> 4);
           if (HEAD && p.x_tf32) {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
@@ -281,8 +285,8 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
       for (int q = 0; q < (HEAD ? 0 : 8); ++q, ++wc) {
         int is_w2, nb;
         ffn_seq(q, is_w2, nb);
-        const int ws = wc % NW, hs = nb & 1;
-        mbar_wait(BAR(B_WFULL + ws), (wc / NW) & 1, 46);
+        const int ws = wc % NWK, hs = nb & 1;
+        mbar_wait(BAR(B_WFULL + ws), (wc / NWK) & 1, 46);
         TT(10 + 4 * q);
         if (!is_w2 && n > 0) {
           // the hidden slots are the previous tile's K / V (or classifier) accumulators: drained?
@@ -293,7 +297,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
         TT(11 + 4 * q);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t w_lo = w_lo0 + (uint32_t)ws * (BLK_BYTES >> 4);
+          const uint32_t w_lo = w_lo0 + (uint32_t)wslot_blk(ws) * (BLK_BYTES >> 4);
           if (!is_w2) {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
@@ -321,15 +325,15 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__
         TT(50);
         ++aln_use;
         for (int j = 0; j < 3; ++j, ++wc) {
-          const int ws = wc % NW;
+          const int ws = wc % NWK;
           const uint32_t r_out = j == 0 ? r_hid[0] : j == 1 ? r_hid[1] : r_acc;
-          mbar_wait(BAR(B_WFULL + ws), (wc / NW) & 1, 51);
+          mbar_wait(BAR(B_WFULL + ws), (wc / NWK) & 1, 51);
           // head mode has no hidden blocks in between: q / k land on the previous tile's k / v accumulators
           if (HEAD && n > 0 && j < 2) mbar_wait(BAR(B_REGFREE + (n + 1 + j) % 3), prev_par, 59);
           TT(52 + 2 * j);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t w_lo = w_lo0 + (uint32_t)ws * (BLK_BYTES >> 4);
+            const uint32_t w_lo = w_lo0 + (uint32_t)wslot_blk(ws) * (BLK_BYTES >> 4);
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
               umma_ts_lh(r_out, t_aln + kk * 8, w_lo + (kk >> 2) * (HALF_BYTES >> 4) + (kk & 3) * 2,
@@ -799,18 +803,20 @@ cudaError_t launch_tail_tc(const TailTcArgs& a, int num_sms, cudaStream_t s, std
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_dev = dev;
   }
   const int n_tiles = (a.M + 127) / 128;
   const int grid = n_tiles < num_sms ? n_tiles : num_sms;
-  static const bool want_trace = getenv("VADB_TAIL_TRACE") != nullptr;
-  if (want_trace && has_qkv && !head) {
+  static const char* want_trace = getenv("VADB_TAIL_TRACE");          // "1": q|k|v variant, "0": last-layer variant
+  if (want_trace && !head && (atoi(want_trace) != 0) == has_qkv) {
     long long* dtr = nullptr;
     cudaMalloc(&dtr, 256 * sizeof(long long));
     cudaMemsetAsync(dtr, 0, 256 * sizeof(long long), s);
     p.trace = dtr;
-    tail_tc_kernel<1, true><<<grid, NTHREADS, SMEM_BYTES, s>>>(to, tq, tk, tv, p);
+    if (has_qkv) tail_tc_kernel<1, true><<<grid, NTHREADS, SMEM_BYTES, s>>>(to, tq, tk, tv, p);
+    else tail_tc_kernel<0, true><<<grid, NTHREADS, SMEM_BYTES, s>>>(to, tq, tk, tv, p);
     long long ht[256];
     cudaMemcpyAsync(ht, dtr, sizeof ht, cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
