@@ -834,6 +834,13 @@ int vadb_forward_ragged(vadb_handle* h, const void* x, int x_dtype, const int32_
     ~WsView() { if (!on) return; h->cap_frames = cap; h->ws_h = hh; h->ws_q = q; h->ws_k = k; h->ws_v = v; h->ws_o = o; h->ws_hid = hid; h->ws_aln = aln; h->ws_prob = pr; }
   };
   const size_t act = is_bf16_mode(h) ? sizeof(bf16) : sizeof(float);
+  // the side streams rejoin the caller's stream on EVERY way out once they have been forked (a failed bucket must not
+  // leave work behind that races with the next call on the shared workspace)
+  auto join = [&]() {
+    if (!concurrent) return;
+    for (int i = 0; i < 2; ++i)
+      if (cudaEventRecord(h->bk_join[i], h->bk_stream[i]) == cudaSuccess) cudaStreamWaitEvent(s, h->bk_join[i], 0);
+  };
   int side = 0;
   for (size_t kk = 0; kk < K; ++kk) {
     const size_t k = K - 1 - kk;
@@ -842,7 +849,7 @@ int vadb_forward_ragged(vadb_handle* h, const void* x, int x_dtype, const int32_
     const int32_t* ids = d_ids + start[k];
     char* xin = (char*)h->bk_x + (concurrent ? in_off[k] : 0);
     cudaError_t e = launch_gather_clips(x, xin, ids, n, T, Tk, (int)(F * xsz), sk);
-    if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("gather: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) { join(); return fail(h, VADB_E_CUDA, std::string("gather: ") + cudaGetErrorString(e)); }
     h->launches++;
     float* pk = (float*)((char*)h->bk_out + (concurrent ? out_off[k] : 0));
     float* lk = pk + (((size_t)n * Tk + 3) & ~(size_t)3);
@@ -850,16 +857,12 @@ int vadb_forward_ragged(vadb_handle* h, const void* x, int x_dtype, const int32_
       WsView view(h, concurrent, ws_off[k], ws_off[k + 1] - ws_off[k], act);
       rc = vadb_forward(h, xin, x_dtype, d_blen + start[k], n, Tk, prob ? pk : nullptr, logp ? lk : nullptr, (void*)sk);
     }
-    if (rc) return rc;
+    if (rc) { join(); return rc; }
     e = launch_scatter_clips(prob ? pk : nullptr, logp ? lk : nullptr, prob, logp, ids, n, T, Tk, sk);
-    if (e != cudaSuccess) return fail(h, VADB_E_CUDA, std::string("scatter: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) { join(); return fail(h, VADB_E_CUDA, std::string("scatter: ") + cudaGetErrorString(e)); }
     h->launches++;
   }
-  if (concurrent)
-    for (int i = 0; i < 2; ++i) {
-      CU_TRY(h, cudaEventRecord(h->bk_join[i], h->bk_stream[i]));
-      CU_TRY(h, cudaStreamWaitEvent(s, h->bk_join[i], 0));
-    }
+  join();
   return VADB_OK;
 }
 
