@@ -83,8 +83,11 @@ struct vadb_handle {
   float* ws_prob = nullptr;
 
   // host-call staging
-  cudaStream_t own_stream = nullptr, own_stream2 = nullptr;
+  cudaStream_t own_stream = nullptr, own_stream2 = nullptr, own_stream3 = nullptr;     // upload, compute, download
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_out[2] = {nullptr, nullptr};        // downloads of the host call that used device output half i have completed
+  long out_seq = 0;                                  // host calls issued so far (selects the output half)
+  size_t last_out_half = 0;                          // floats per output half of the previous host call
   cudaEvent_t ev_call[4] = {nullptr, nullptr, nullptr, nullptr};   // completion of the last four asynchronous host calls
   long call_seq = 0, chunk_seq = 0;
   long waited_upto = -1;     // every asynchronous host call with ticket <= waited_upto is known to have completed
@@ -513,6 +516,8 @@ int vadb_create(vadb_handle** out, const vadb_config* cfg, int device) {
   DeviceGuard dg(device);
   e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream3, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming);
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
@@ -556,6 +561,8 @@ void vadb_destroy(vadb_handle* h) {
   if (h->bk_fork) cudaEventDestroy(h->bk_fork);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->own_stream2) cudaStreamDestroy(h->own_stream2);
+  if (h->own_stream3) cudaStreamDestroy(h->own_stream3);
+  for (int i = 0; i < 2; ++i) if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
@@ -883,7 +890,9 @@ static int forward_host_impl(vadb_handle* h, const void* x, int x_dtype, const i
   DeviceGuard dg(h->device);
   // Chunked two-stream pipeline: the H2D copy of clip chunk i+1 overlaps the forward of chunk i
   // (the reference does one blocking .to(device) per 1000-window chunk, vad/predictor.py:223).
-  cudaStream_t s_copy = h->own_stream, s_comp = h->own_stream2;
+  // Three streams: uploads, forwards, downloads.  The download of call i runs beside the forward of call i+1 (two
+  // device output halves alternate per call), so the compute stream carries kernels only.
+  cudaStream_t s_copy = h->own_stream, s_comp = h->own_stream2, s_down = h->own_stream3;
   const int F = h->cfg.feature_size;
   const size_t clip_in = (size_t)T * F * (x_dtype == VADB_BF16 ? sizeof(bf16) : sizeof(float));
   // >= 8 MB per chunk, at most 4 chunks: enough overlap, few (small, launch-bound) forward passes
@@ -919,7 +928,8 @@ static int forward_host_impl(vadb_handle* h, const void* x, int x_dtype, const i
   if (!in_pinned && (rc = ensure_bytes(h, &h->pin_in, &h->pin_in_bytes, 2 * chunk_in, true))) return rc;
   if (!out_pinned && (rc = ensure_bytes(h, &h->pin_out, &h->pin_out_bytes, n * 3 * sizeof(float), true))) return rc;
   if ((rc = ensure_bytes(h, &h->dev_in, &h->dev_in_bytes, 2 * chunk_in, false))) return rc;
-  if ((rc = ensure_bytes(h, &h->dev_out, &h->dev_out_bytes, (n * 3 + 4) * sizeof(float), false))) return rc;
+  const size_t out_half = (n * 3 + 4 + 3) & ~(size_t)3;       // floats per output half
+  if ((rc = ensure_bytes(h, &h->dev_out, &h->dev_out_bytes, 2 * out_half * sizeof(float), false))) return rc;
   if ((rc = ensure_pe(h, T))) return rc;
   if ((rc = ensure_workspace(h, (size_t)std::min(C, clips_per_pass(C, T)) * T))) return rc;
   int32_t* dlen = nullptr;
@@ -933,8 +943,16 @@ static int forward_host_impl(vadb_handle* h, const void* x, int x_dtype, const i
     CU_TRY(h, cudaMemcpyAsync(h->dev_len, lengths, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, s_comp));
     dlen = h->dev_len;
   }
-  float* dprob = (float*)h->dev_out;
+  const int oslot = (int)(h->out_seq++ & 1);
+  float* dprob = (float*)h->dev_out + (size_t)oslot * out_half;
   float* dlogp = dprob + ((n + 3) & ~(size_t)3);       // 16-byte aligned for any B*T (the fused classifier stores float2)
+  // this output half was last used two calls ago: its downloads must have finished before a forward writes it again
+  // (a call of another size lays the halves out differently: then wait for the previous call's downloads too)
+  CU_TRY(h, cudaStreamWaitEvent(s_comp, h->ev_out[oslot], 0));
+  if (out_half != h->last_out_half) {
+    CU_TRY(h, cudaStreamWaitEvent(s_comp, h->ev_out[oslot ^ 1], 0));
+    h->last_out_half = out_half;
+  }
   float* hprob = out_pinned ? prob : (float*)h->pin_out;
   float* hlogp = out_pinned ? logp : (float*)h->pin_out + n;
   for (int i = 0; i < n_chunks; ++i) {
@@ -961,17 +979,20 @@ static int forward_host_impl(vadb_handle* h, const void* x, int x_dtype, const i
                            logp ? dlogp + (size_t)b0 * T * 2 : nullptr, s_comp)))
       return rc;
     CU_TRY(h, cudaEventRecord(h->ev_done[slot], s_comp));
+    CU_TRY(h, cudaStreamWaitEvent(s_down, h->ev_done[slot], 0));
     if (prob) CU_TRY(h, cudaMemcpyAsync(hprob + (size_t)b0 * T, dprob + (size_t)b0 * T, (size_t)Bc * T * sizeof(float),
-                                        cudaMemcpyDeviceToHost, s_comp));
+                                        cudaMemcpyDeviceToHost, s_down));
     if (logp) CU_TRY(h, cudaMemcpyAsync(hlogp + (size_t)b0 * T * 2, dlogp + (size_t)b0 * T * 2,
-                                        (size_t)Bc * T * 2 * sizeof(float), cudaMemcpyDeviceToHost, s_comp));
+                                        (size_t)Bc * T * 2 * sizeof(float), cudaMemcpyDeviceToHost, s_down));
   }
   h->chunk_seq += n_chunks;
+  CU_TRY(h, cudaEventRecord(h->ev_out[oslot], s_down));
   if (ticket) {                      // results land in the caller's pinned buffers; vadb_host_wait(ticket)
-    CU_TRY(h, cudaEventRecord(h->ev_call[h->call_seq & 3], s_comp));
+    CU_TRY(h, cudaEventRecord(h->ev_call[h->call_seq & 3], s_down));     // downloads complete in call order
     *ticket = h->call_seq++;
     return VADB_OK;
   }
+  CU_TRY(h, cudaStreamSynchronize(s_down));
   CU_TRY(h, cudaStreamSynchronize(s_comp));
   CU_TRY(h, cudaStreamSynchronize(s_copy));
   h->waited_upto = h->call_seq - 1;       // earlier asynchronous calls ran on the same streams: all complete
