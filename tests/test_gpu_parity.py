@@ -539,3 +539,24 @@ def test_ragged_forward_concurrent_buckets_equal_sequential(monkeypatch):
         outs.append((prob.cpu().numpy().copy(), logp.cpu().numpy().copy()))
     for p, lp in outs[1:]:
         assert np.array_equal(p, outs[0][0], equal_nan=True) and np.array_equal(lp, outs[0][1], equal_nan=True)
+
+
+def test_forward_async_mixed_sizes_share_the_output_halves():
+    """Asynchronous host calls of different sizes back to back: downloads run on their own stream from two device
+    output halves whose layout depends on the call's size, so a call of another size must wait for the previous
+    call's downloads before its forward overwrites the region (results identical to the blocking call)."""
+    eng = engine_for(SYN, "bf16")
+    shapes = [(24, 128), (8, 128), (24, 128), (3, 256), (40, 128), (8, 128), (24, 128), (1, 128)]
+    xs = [O.make_input(70 + i, b, t, 64).pin_memory() for i, (b, t) in enumerate(shapes)]
+    want = [tuple(o.clone() for o in eng.forward(x)) for x in xs]
+    for rep in range(3):
+        pending, got = [], []
+        for x in xs:
+            pending.append(eng.forward_async(x, want_logp=True))
+            if len(pending) > 3:
+                got.append(tuple(o.clone() for o in pending.pop(0).wait()))
+        while pending:
+            got.append(tuple(o.clone() for o in pending.pop(0).wait()))
+        for (p, lp), (wp, wlp) in zip(got, want):
+            torch.testing.assert_close(p, wp, rtol=0, atol=0)
+            torch.testing.assert_close(lp, wlp, rtol=0, atol=0)
