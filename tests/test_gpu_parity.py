@@ -560,3 +560,41 @@ def test_forward_async_mixed_sizes_share_the_output_halves():
         for (p, lp), (wp, wlp) in zip(got, want):
             torch.testing.assert_close(p, wp, rtol=0, atol=0)
             torch.testing.assert_close(lp, wlp, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_random_shapes_against_oracle(seed):
+    """Randomised shapes through every entry route of the forward: batch size, frame count (tile multiples and not),
+    feature width, number of layers, compute dtype, feature dtype, no mask / device lengths (padded batch) / host
+    lengths (length-bucketed, concurrent buckets) -- every clip over its valid frames against the oracle run on the
+    clip alone."""
+    import random
+    from vad_b200.engine import VadEngine
+    rnd = random.Random(1000 + seed)
+    F = rnd.choice((8, 40, 64, 80, 128))
+    L = rnd.choice((1, 2, 3, 4))
+    B = rnd.randint(1, 12)
+    T = rnd.choice((1, 7, 64, 127, 128, 129, 256, 300, 384, 512, 640))
+    dtype = "fp32" if (seed % 5 == 4 and B * T <= 2048) else "bf16"
+    st = O.make_state(200 + seed, F, L, 128)
+    eng = VadEngine.from_state_dict(st, compute_dtype=dtype)
+    x = O.make_input(300 + seed, B, T, F)
+    mode = rnd.choice(("none", "device", "host"))
+    lengths = [T] * B if mode == "none" else [rnd.randint(1, T) for _ in range(B)]
+    xin = x.to(torch.bfloat16) if (dtype == "bf16" and rnd.random() < 0.5) else x
+    if mode == "none":
+        prob, logp = eng.forward(xin.cuda())
+    elif mode == "device":
+        prob, logp = eng.forward(xin.cuda(), torch.tensor(lengths, dtype=torch.int32).cuda())
+    else:
+        prob, logp = eng.forward(xin.cuda(), np.asarray(lengths, dtype=np.int32))
+    p, lp = prob.cpu().numpy(), logp.cpu().numpy()
+    worst = 0.0
+    for b, n in enumerate(lengths):
+        want = O.forward_prob(st, xin[b:b + 1, :n].float()).numpy()[0]
+        worst = max(worst, float(np.abs(p[b, :n] - want).max()))
+        # the module's log-probabilities are consistent with the probabilities
+        np.testing.assert_allclose(np.exp(lp[b, :n, 1]), p[b, :n], atol=2e-6, rtol=1e-5)
+    print(f"seed {seed}: F={F} L={L} B={B} T={T} {dtype} lengths={mode} x={xin.dtype}: max|dP| = {worst:.3e}")
+    assert worst <= TOL[dtype]
+    eng.close()
