@@ -17,7 +17,10 @@
  *     to take that out of the steady state).
  *   - the caller owns inputs/outputs; the library owns weights, the positional-encoding
  *     table and the workspace inside the handle.  One handle per device; a handle is not
- *     thread-safe, distinct handles are independent.
+ *     thread-safe, distinct handles are independent.  All calls on one handle share its workspace:
+ *     stream-taking calls must be issued on ONE stream at a time (or be ordered by the caller), the
+ *     host-buffer calls (vadb_*_host*) run on the library's own streams and order themselves --
+ *     a blocking host call first completes any asynchronous one that is still in flight.
  *   - there is NO CPU fallback: without a CUDA device vadb_create fails.
  */
 #ifndef VADB200_H_

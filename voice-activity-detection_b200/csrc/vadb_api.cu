@@ -1095,10 +1095,22 @@ int vadb_predict_probabilities(vadb_handle* h, const float* feat, int L, int hal
   return VADB_OK;
 }
 
+// The blocking host entry points below share the staging buffers and the workspace with vadb_forward_host_async: any
+// asynchronous call that is still in flight is completed first.
+static int drain_async_host_calls(vadb_handle* h) {
+  if (h->call_seq - 1 <= h->waited_upto) return VADB_OK;
+  DeviceGuard dg(h->device);
+  CU_TRY(h, cudaStreamSynchronize(h->own_stream2));
+  CU_TRY(h, cudaStreamSynchronize(h->own_stream3));
+  h->waited_upto = h->call_seq - 1;
+  return VADB_OK;
+}
+
 int vadb_predict_probabilities_host(vadb_handle* h, const float* feat, int L, int half, int jump,
                                     float* probs_LW, float* mean_L) {
   int rc = check_ready(h);
   if (rc) return rc;
+  if ((rc = drain_async_host_calls(h))) return rc;
   if (!feat || L < 0 || half < 1 || jump < 1) return fail(h, VADB_E_INVALID, "bad window arguments");
   if (L == 0) return VADB_OK;
   DeviceGuard dg(h->device);
@@ -1198,6 +1210,7 @@ int vadb_predict_audio_host(vadb_handle* h, const float* audio, long n_samples, 
   int rc = check_ready(h);
   if (rc) return rc;
   if (!audio || n_samples <= 0 || hop <= 0 || half < 1 || jump < 1) return fail(h, VADB_E_INVALID, "bad audio arguments");
+  if ((rc = drain_async_host_calls(h))) return rc;
   DeviceGuard dg(h->device);
   cudaStream_t s = h->own_stream;
   const int F = h->cfg.feature_size, W = window_W(half, jump);
