@@ -103,7 +103,9 @@ int vadb_forward(vadb_handle* h, const void* x, int x_dtype, const int32_t* leng
  * with its own key-padding mask, so per-frame kernels and attention see only the frames each clip needs instead of
  * the batch maximum T (vad/modeling/transformer.py:432-447 builds one [B, T] mask for the padded batch).  Valid
  * frames (t < lengths[b]) get exactly the results of vadb_forward; frames past a clip's processed length, which
- * the reference computes from the padding, are returned as 0.
+ * the reference computes from the padding, are returned as 0.  The groups run concurrently: two library-owned side
+ * streams fork from `stream` after the call's prologue and rejoin it before the call returns, so for the caller the
+ * call is ordered on `stream` like any other.
  *  x             dev [B,T,F] padded batch        lengths_host  HOST int32 [B]        prob / logp  dev, as above */
 int vadb_forward_ragged(vadb_handle* h, const void* x, int x_dtype, const int32_t* lengths_host,
                         int B, int T, float* prob, float* logp, void* stream);
