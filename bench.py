@@ -457,10 +457,18 @@ def main():
         n_sets = 3 if args.config == 2 else 2
         for _ in range(n_sets):      # 3 x (q,k,v,o) = 3 x 134 MB (bf16) > L2
             qkv_sets.append(tuple(torch.randn(Bq, Tq, D, generator=gg).to(dev).to(in_dtype) for _ in range(3)))
+        # The peak this is compared with is a burst figure (MEASURED_PEAKS.json: best of 10 copies on an idle GPU), so
+        # the kernel is timed the same way: alone, a short burst after the GPU has idled for half a second (the forward
+        # loops above leave it under sw_power_cap).  The same kernel launched back to back for >= 0.3 s is reported
+        # beside it ("sustained").
+        torch.cuda.synchronize()
+        time.sleep(0.5)
         for i in range(3):
             eng.attention(*qkv_sets[i % n_sets])
         attn_iters = 20 if args.config == 2 else 5
-        ms_attn = timed(lambda i: eng.attention(*qkv_sets[i % n_sets]), attn_iters) / attn_iters
+        ms_attn = min(timed(lambda i: eng.attention(*qkv_sets[i % n_sets]), attn_iters) / attn_iters for _ in range(3))
+        sus_iters = max(attn_iters, int(0.3e3 / max(ms_attn, 1e-3)))
+        ms_attn_sus = timed(lambda i: eng.attention(*qkv_sets[i % n_sets]), sus_iters) / sus_iters
         esz = 2 if args.dtype == "bf16" else 4
         alg_bytes = 4 * Bq * Tq * D * esz                  # read Q,K,V + write O once
         alg_flops = 4 * Bq * Tq * Tq * D                    # QK^T + PV
@@ -478,6 +486,11 @@ def main():
                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "traffic": traffic if args.config == 2 else None, "traffic_source": traffic_src,
                     "peak_source": peak_src, "us_per_launch": ms_attn * 1e3, "algorithmic_bytes": alg_bytes,
+                    "method": f"kernel alone, CUDA events, best of 3 bursts of {attn_iters} launches after 0.5 s idle "
+                              "(the peak is a best-of-10 burst too); inputs rotated over sets larger than L2",
+                    "sustained": {"us_per_launch": ms_attn_sus * 1e3, "launches": sus_iters,
+                                  "achieved": alg_bytes / (ms_attn_sus * 1e-3) / 1e9,
+                                  "frac": alg_bytes / (ms_attn_sus * 1e-3) / 1e9 / hbm_peak},
                     "tensor": {"achieved": alg_flops / (ms_attn * 1e-3) / 1e12, "peak": tf_peak,
                                "unit": "TFLOP/s", "frac": alg_flops / (ms_attn * 1e-3) / 1e12 / tf_peak}}
         del qkv_sets
