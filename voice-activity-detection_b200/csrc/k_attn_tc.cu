@@ -126,7 +126,7 @@ __device__ __forceinline__ Item get_item(int idx, int n_full, int npairs, int T,
 //          rel. error 7.5e-5, far below the bf16 rounding of P) instead of the SFU: 0, 1/4, 3/8, 1/2
 //   bit 4  no SFU token (the warpgroups run free)
 //   bits 5-6  element index of the early hand-over: 46, 30, 16
-#define VADB_ATTN_VARIANTS(X) X(0) X(1) X(20) X(24) X(28) X(12) X(8)
+#define VADB_ATTN_VARIANTS(X) X(0) X(1)
 constexpr int ATTN_DEFAULT_VARIANT = 0;      // re-timed at the end of round 2: 0 is 0.5 % faster than the early hand-over (1)
 constexpr int ATTN_DEFAULT_STAGGER = 1;
 template <int VAR> __device__ __forceinline__ bool use_poly(int i) {
