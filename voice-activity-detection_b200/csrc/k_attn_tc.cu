@@ -439,11 +439,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         const bool work = j >= 0, has_next = j + 1 < nkv;
         const uint32_t tsb = ts + (g & 1) * 64;
         uint32_t pk[32];
-        bool o_ready = true, rescale = false;
+        bool o_ready = true, rescale = false, s_ready = false;
         if (work) {
           TS(0);
-          // non-blocking probe, consumed after the exponentials: "P V of the previous step retired"
-          o_ready = (j == 0) || mbar_test_wait(BAR(B_OFULL + t), (g - 1) & 1);
+          // (the two non-blocking barrier probes of a step -- "P V of the previous step retired", "scores of the next
+          // step are in TMEM" -- are issued half way through the exponentials, in the shadow of the SFU, instead of
+          // on the serial chain in front of / behind them: see the exps lambda)
           const int kbase = j * BKV;
           if (kbase + BKV > len) {           // warp-uniform: only the last tile holds masked keys
 #pragma unroll
@@ -469,6 +470,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
               mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(s0, s1));
               pk[i >> 1] = pack_bf16(p0, p1);
               if (i == 62) p_last = p1;
+              if (i == 32 && pinned) {
+                o_ready = (j == 0) || mbar_test_wait(BAR(B_OFULL + t), (g - 1) & 1);
+                s_ready = has_next && mbar_test_wait(BAR(B_SFULL + 2 * t + ((g + 1) & 1)), ((g + 1) >> 1) & 1);
+              }
               if ((VAR & 1) && pinned && i == early_idx<VAR>() && pingpong) {
                 scratch[8 + (threadIdx.x & 7)] = p0;
                 nbar_arrive(t == 0 ? NB_TOKEN1 : NB_TOKEN0, 256);
@@ -537,7 +542,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         const int gn = work ? g + 1 : g;
         const uint32_t tsn = ts + (gn & 1) * 64;
         bool s_loaded = false;
-        if (has_next && work && mbar_test_wait(BAR(B_SFULL + 2 * t + (gn & 1)), (gn >> 1) & 1)) {
+        if (has_next && work && s_ready) {
           tc_fence_after();
           tmem_ld32(tsn, sv[0]);
           tmem_ld32(tsn + 32, sv[1]);
